@@ -1,0 +1,821 @@
+// capi.cu — the extern "C" surface of libdtree_b200.so (include/dtree_b200.h): handle state,
+// device mirror of the tree, scratch management and kernel launches. No sampling or social-choice
+// arithmetic runs on the host: if CUDA is unusable every sampling entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dtree_b200.h"
+#include "dtree_b200_debug.h"
+#include "host_tree.h"
+#include "launch.h"
+
+using namespace dtb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) return fail(DTREE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;  // elements allocated
+  cudaError_t reserve(size_t want) {
+    if (want <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (want == 0) want = 1;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T> &v, cudaStream_t s) {
+    cudaError_t e = reserve(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (dev == prev) || cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Packs ballot `b[0..len)` (truncated to nc-1 preferences: the last one can never matter to
+// IRV) into 3 words; unused positions up to nc-1 repeat the first candidate, which is how the
+// IRV kernel recognises the end of an observed ballot without a length array.
+void pack_ballot(const uint8_t *b, uint32_t len, uint32_t nc, bool pad_with_first, uint64_t out[kMaxKeyWords],
+                 uint32_t *packed_len) {
+  BallotKey<kMaxKeyWords> k;
+  for (int w = 0; w < kMaxKeyWords; ++w) k.w[w] = 0;
+  uint32_t L = std::min(len, nc - 1);
+  for (uint32_t j = 0; j < L; ++j) key_set<kMaxKeyWords>(k, (int)j, b[j]);
+  if (pad_with_first && L > 0)
+    for (uint32_t j = L; j < nc - 1; ++j) key_set<kMaxKeyWords>(k, (int)j, b[0]);
+  for (int w = 0; w < kMaxKeyWords; ++w) out[w] = k.w[w];
+  if (packed_len) *packed_len = L;
+}
+
+double falling_factorial(uint32_t n, uint32_t k) {
+  double r = 1.0;
+  for (uint32_t i = 0; i < k; ++i) r *= (double)(n - i);
+  return r;
+}
+
+}  // namespace
+
+struct dtree_ballots {
+  std::vector<uint8_t> prefs;
+  std::vector<uint64_t> offsets{0};
+  std::vector<uint32_t> counts;
+};
+
+struct dtree {
+  HostTree tree;
+  int device;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  // device mirror
+  uint64_t mirrored_version = ~0ull;
+  FlatTree flat;
+  DevBuf<uint32_t> d_node_base, d_slot_count, d_obs_cnt, d_obs_tally0;
+  DevBuf<int32_t> d_slot_child;
+  DevBuf<uint8_t> d_slot_cand, d_obs_first;
+  DevBuf<uint64_t> d_obs_key;
+  uint32_t n_obs_entries = 0;
+  // scratch + small device state
+  DevBuf<uint8_t> d_scratch;
+  DevBuf<unsigned long long> d_wins, d_stats;
+  DevBuf<unsigned int> d_counter;
+  DevBuf<int> d_error;
+  DevBuf<uint32_t> d_entry_count;
+  DevBuf<uint8_t> d_orders;
+  // tuning
+  int block_threads = 0, blocks_per_sm = 0;
+  uint32_t urn_max = 8;
+  // callbacks, stats
+  int (*should_abort)(void *) = nullptr;
+  void *abort_user = nullptr;
+  uint64_t stats[16] = {0};
+
+  dtree(const HostParams &p, int dev) : tree(p), device(dev) {}
+};
+
+namespace {
+
+DeviceParams device_params(const HostParams &P) {
+  DeviceParams D;
+  memset(&D, 0, sizeof D);
+  D.nc = P.nc;
+  D.min_depth = P.min_depth;
+  D.max_depth = P.max_depth;
+  D.leaf_depth = P.max_depth - 1u;  // unsigned wrap when max_depth == 0, as in irv_node.cpp:136
+  D.small_alpha = 0;
+  for (uint32_t d = 0; d < kMaxCandidates; ++d) {
+    double a = P.a0;
+    if (P.vd) a *= (d < P.depth_factors.size()) ? P.depth_factors[d] : 1.0;
+    D.a_prior[d] = (float)a;
+    if (d + 1 < P.nc && a < 1.0) D.small_alpha = 1;
+  }
+  return D;
+}
+
+int ensure_mirror(dtree *t, cudaStream_t s) {
+  if (t->mirrored_version == t->tree.version()) return DTREE_OK;
+  t->tree.flatten(t->flat);
+  const FlatTree &F = t->flat;
+  const uint32_t nc = t->tree.P.nc;
+  const int W = key_words_for(nc);
+  if (F.slot_count.size() >= 0xFFFFFFF0ull) return fail(DTREE_ERR_STATE, "tree has too many outcome slots for 32-bit indices");
+  CUDA_TRY(t->d_node_base.upload(F.node_base, s));
+  CUDA_TRY(t->d_slot_count.upload(F.slot_count, s));
+  CUDA_TRY(t->d_slot_child.upload(F.slot_child, s));
+  CUDA_TRY(t->d_slot_cand.upload(F.slot_cand, s));
+  // observed entries for the IRV stage
+  size_t n = F.obs_counts.size();
+  std::vector<uint64_t> keys(n * W);
+  std::vector<uint8_t> first(n);
+  std::vector<uint32_t> tally0(kMaxCandidates, 0);
+  for (size_t i = 0; i < n; ++i) {
+    uint64_t k[kMaxKeyWords];
+    uint32_t len = (uint32_t)(F.obs_offsets[i + 1] - F.obs_offsets[i]);
+    pack_ballot(F.obs_prefs.data() + F.obs_offsets[i], len, nc, true, k, nullptr);
+    for (int w = 0; w < W; ++w) keys[i * W + w] = k[w];
+    first[i] = len ? F.obs_prefs[F.obs_offsets[i]] : 0xFF;
+    if (len) tally0[first[i]] += F.obs_counts[i];
+  }
+  CUDA_TRY(t->d_obs_key.upload(keys, s));
+  CUDA_TRY(t->d_obs_cnt.upload(F.obs_counts, s));
+  CUDA_TRY(t->d_obs_first.upload(first, s));
+  CUDA_TRY(t->d_obs_tally0.upload(tally0, s));
+  t->n_obs_entries = (uint32_t)n;
+  t->stats[8] += (F.node_base.size() + F.slot_count.size() + F.slot_child.size()) * 4 + F.slot_cand.size() +
+                 keys.size() * 8 + n * 5 + kMaxCandidates * 4;
+  CUDA_TRY(cudaStreamSynchronize(s));  // the host vectors above die with this frame
+  t->mirrored_version = t->tree.version();
+  return DTREE_OK;
+}
+
+struct Plan {
+  int W, block, grid, blocks_per_sm;
+  bool log_gamma;
+  uint32_t cap_items, cap_entries;
+  uint64_t stride;
+};
+
+template <int W>
+uint64_t scratch_bytes(uint32_t ci, uint32_t ce, uint32_t nobs) { return Scratch<W>::bytes(ci, ce, nobs); }
+
+int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, Plan &pl) {
+  const HostParams &P = t->tree.P;
+  const uint32_t nc = P.nc;
+  pl.W = key_words_for(nc);
+  DeviceParams D = device_params(P);
+  pl.log_gamma = D.small_alpha != 0;
+  // Upper bounds on what one election can hold: never more things than ballots, never more than
+  // there are distinct prefixes.
+  uint32_t item_depth = std::min<uint32_t>(D.leaf_depth, nc - 2);          // deepest frontier
+  uint32_t max_len = std::min<uint32_t>(P.max_depth ? P.max_depth : nc, nc - 1);  // longest sampled ballot
+  double items = std::min<double>((double)n_sample, falling_factorial(nc, item_depth));
+  double entries = 0;
+  for (uint32_t l = 0; l <= max_len; ++l) entries += falling_factorial(nc, l);
+  entries = std::min<double>((double)n_sample, entries);
+  pl.cap_items = (uint32_t)std::max(items, 1.0);
+  pl.cap_entries = (uint32_t)std::max(entries, 1.0);
+  uint32_t nobs = use_obs ? t->n_obs_entries : 0;
+  pl.stride = pl.W == 1 ? scratch_bytes<1>(pl.cap_items, pl.cap_entries, nobs)
+            : pl.W == 2 ? scratch_bytes<2>(pl.cap_items, pl.cap_entries, nobs)
+                        : scratch_bytes<3>(pl.cap_items, pl.cap_entries, nobs);
+  pl.stride = (pl.stride + 255) & ~255ull;
+
+  int block = t->block_threads;
+  if (block == 0) {
+    // A block works on one election; size it to the widest frontier it is likely to see.
+    double work = std::min<double>(items, 1.0 + (double)t->tree.n_nodes() + (double)n_sample / 8);
+    block = work <= 48 ? 32 : work <= 512 ? 64 : work <= 8192 ? 128 : 256;
+  }
+  bool okb = false;
+  for (int i = 0; i < kNumBlockSizes; ++i) okb |= (kBlockSizes[i] == block);
+  if (!okb) return fail(DTREE_ERR_ARG, "block_threads must be one of 32, 64, 128, 256");
+  if (simulate_smem_bytes(nc, block) + 8192 > t->smem_optin)
+    return fail(DTREE_ERR_CUDA, "not enough shared memory per block");
+  pl.block = block;
+  int occ = pl.W == 1 ? simulate_blocks_per_sm<1>(nc, block, pl.log_gamma)
+          : pl.W == 2 ? simulate_blocks_per_sm<2>(nc, block, pl.log_gamma)
+                      : simulate_blocks_per_sm<3>(nc, block, pl.log_gamma);
+  if (occ <= 0) return fail(DTREE_ERR_CUDA, "kernel cannot be resident (occupancy query failed: %s)",
+                            cudaGetErrorString(cudaGetLastError()));
+  if (t->blocks_per_sm > 0) occ = std::min(occ, t->blocks_per_sm);
+  pl.blocks_per_sm = occ;
+  uint64_t grid = (uint64_t)occ * t->sm_count;
+  grid = std::min<uint64_t>(grid, n_elections);
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  uint64_t budget = (uint64_t)((double)(free_b + t->d_scratch.n) * 0.6);
+  uint64_t fit = std::max<uint64_t>(1, budget / pl.stride);
+  grid = std::max<uint64_t>(1, std::min(grid, fit));
+  if (pl.stride > budget) return fail(DTREE_ERR_CUDA, "one election needs %llu bytes of scratch, more than the device has free",
+                                      (unsigned long long)pl.stride);
+  pl.grid = (int)grid;
+  return DTREE_OK;
+}
+
+void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
+  memset(&a, 0, sizeof a);
+  a.P = device_params(t->tree.P);
+  a.T.node_base = t->d_node_base.p;
+  a.T.slot_count = t->d_slot_count.p;
+  a.T.slot_child = t->d_slot_child.p;
+  a.T.slot_cand = t->d_slot_cand.p;
+  a.T.n_nodes = t->flat.n_nodes();
+  a.urn_max = t->urn_max;
+  a.scratch = t->d_scratch.p;
+  a.scratch_stride = pl.stride;
+  a.cap_items = pl.cap_items;
+  a.cap_entries = pl.cap_entries;
+  a.work_counter = t->d_counter.p;
+  a.error_flag = t->d_error.p;
+  a.stats = t->d_stats.p;
+}
+
+cudaError_t launch(const Plan &pl, const SimArgs &a, cudaStream_t s) {
+  LaunchCfg cfg{pl.block, pl.log_gamma, pl.grid, s};
+  return pl.W == 1 ? launch_simulate<1>(a, cfg) : pl.W == 2 ? launch_simulate<2>(a, cfg) : launch_simulate<3>(a, cfg);
+}
+
+int check_sampling_args(dtree *t, uint32_t n_ballots, const char *seed, size_t seed_len) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  if (!seed && seed_len) return fail(DTREE_ERR_ARG, "null seed");
+  if (t->tree.P.vd && t->tree.P.max_depth == 0)
+    return fail(DTREE_ERR_ARG, "vd requires max_depth >= 1 (the reference reads depthFactors out of bounds here)");
+  (void)n_ballots;
+  return DTREE_OK;
+}
+
+// Common body of the two sample_posterior entry points. d_wins must be device memory on t->device.
+int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots, uint32_t n_winners,
+                  int replace, const char *seed, size_t seed_len, unsigned long long *d_wins, uint8_t *h_orders,
+                  cudaStream_t s, bool sync_at_end) {
+  int rc = check_sampling_args(t, n_ballots, seed, seed_len);
+  if (rc) return rc;
+  const uint32_t nc = t->tree.P.nc;
+  if ((uint64_t)n_ballots < t->tree.n_observed())  // R_tree.cpp:183-186
+    return fail(DTREE_ERR_STATE, "`nBallots` must be larger than the number of ballots observed to obtain the posterior.");
+  if (n_winners < 1 || n_winners >= nc) return fail(DTREE_ERR_ARG, "n_winners must be in [1, n_candidates)");
+  if (n_elections == 0) return DTREE_OK;
+  rc = ensure_mirror(t, s);
+  if (rc) return rc;
+  const bool use_obs = !replace;
+  const uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->tree.n_observed();
+  Plan pl;
+  rc = make_plan(t, n_sample, n_elections, use_obs, pl);
+  if (rc) return rc;
+  CUDA_TRY(t->d_scratch.reserve(pl.stride * pl.grid));
+  CUDA_TRY(t->d_counter.reserve(1));
+  CUDA_TRY(t->d_error.reserve(1));
+  CUDA_TRY(t->d_stats.reserve(kStatCount));
+  CUDA_TRY(cudaMemsetAsync(t->d_error.p, 0, sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(t->d_stats.p, 0, kStatCount * sizeof(unsigned long long), s));
+  if (h_orders) CUDA_TRY(t->d_orders.reserve((size_t)n_elections * nc));
+
+  SimArgs a;
+  fill_args(t, pl, a);
+  a.obs_key = t->d_obs_key.p;
+  a.obs_cnt = t->d_obs_cnt.p;
+  a.obs_first = t->d_obs_first.p;
+  a.obs_tally0 = t->d_obs_tally0.p;
+  a.n_obs = use_obs ? t->n_obs_entries : 0;
+  a.seed = hash_seed(seed, seed_len);
+  a.n_sample = n_sample;
+  a.n_winners = n_winners;
+  a.run_irv = 1;
+  a.win_counts = d_wins;
+
+  // One launch per wave. Without an abort callback the whole range is one wave.
+  uint32_t wave = n_elections;
+  if (t->should_abort) wave = (uint32_t)std::min<uint64_t>(n_elections, (uint64_t)pl.grid * 64);
+  uint64_t launches = 0;
+  for (uint32_t done = 0; done < n_elections; done += wave) {
+    uint32_t n = std::min(wave, n_elections - done);
+    if (t->should_abort && done > 0) {
+      CUDA_TRY(cudaStreamSynchronize(s));
+      if (t->should_abort(t->abort_user)) return fail(DTREE_ERR_ABORTED, "aborted by the host");
+    }
+    a.first_election = first_election + done;
+    a.n_elections = n;
+    a.elim_orders = h_orders ? t->d_orders.p + (size_t)done * nc : nullptr;
+    CUDA_TRY(cudaMemsetAsync(t->d_counter.p, 0, sizeof(unsigned int), s));
+    CUDA_TRY(launch(pl, a, s));
+    ++launches;
+  }
+  t->stats[0] = launches;
+  t->stats[1] = n_elections;
+  t->stats[7] = pl.stride * pl.grid;
+  if (!sync_at_end) return DTREE_OK;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  int err = 0;
+  unsigned long long st[kStatCount];
+  CUDA_TRY(cudaMemcpy(&err, t->d_error.p, sizeof err, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(st, t->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
+  if (err) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
+  t->stats[2] = st[kStatEntries];
+  t->stats[3] = st[kStatItems];
+  t->stats[4] = st[kStatGammas];
+  t->stats[5] = st[kStatBinomials];
+  t->stats[6] = st[kStatRereads];
+  t->stats[10] = st[kStatSlots];
+  t->stats[11] = st[kStatUrnItems];
+  if (h_orders) {
+    CUDA_TRY(cudaMemcpy(h_orders, t->d_orders.p, (size_t)n_elections * nc, cudaMemcpyDeviceToHost));
+    t->stats[9] += (uint64_t)n_elections * nc;
+  }
+  return DTREE_OK;
+}
+
+// Expansion of ONE election without IRV; copies the sampled entries back.
+int run_dump(dtree *t, uint64_t election, uint32_t n_sample, const char *seed, size_t seed_len, dtree_ballots *out) {
+  const uint32_t nc = t->tree.P.nc;
+  cudaStream_t s = 0;
+  int rc = ensure_mirror(t, s);
+  if (rc) return rc;
+  Plan pl;
+  rc = make_plan(t, n_sample, 1, false, pl);
+  if (rc) return rc;
+  pl.grid = 1;
+  CUDA_TRY(t->d_scratch.reserve(pl.stride));
+  CUDA_TRY(t->d_counter.reserve(1));
+  CUDA_TRY(t->d_error.reserve(1));
+  CUDA_TRY(t->d_stats.reserve(kStatCount));
+  CUDA_TRY(t->d_entry_count.reserve(1));
+  CUDA_TRY(t->d_wins.reserve(kMaxCandidates));
+  CUDA_TRY(cudaMemsetAsync(t->d_error.p, 0, sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(t->d_counter.p, 0, sizeof(unsigned int), s));
+  CUDA_TRY(cudaMemsetAsync(t->d_entry_count.p, 0, sizeof(uint32_t), s));
+  CUDA_TRY(cudaMemsetAsync(t->d_stats.p, 0, kStatCount * sizeof(unsigned long long), s));
+  SimArgs a;
+  fill_args(t, pl, a);
+  a.seed = hash_seed(seed, seed_len);
+  a.first_election = election;
+  a.n_elections = 1;
+  a.n_sample = n_sample;
+  a.n_winners = 1;
+  a.run_irv = 0;
+  a.win_counts = t->d_wins.p;
+  a.entry_count_out = t->d_entry_count.p;
+  CUDA_TRY(launch(pl, a, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  int err = 0;
+  uint32_t n = 0;
+  CUDA_TRY(cudaMemcpy(&err, t->d_error.p, sizeof err, cudaMemcpyDeviceToHost));
+  if (err) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
+  CUDA_TRY(cudaMemcpy(&n, t->d_entry_count.p, sizeof n, cudaMemcpyDeviceToHost));
+  const int W = pl.W;
+  std::vector<uint64_t> keys((size_t)n * W + 1);
+  std::vector<uint32_t> cnt(n + 1);
+  std::vector<uint8_t> len(n + 1);
+  // scratch layout of block 0 (Scratch<W>::bind)
+  uint8_t *base = t->d_scratch.p;
+  uint8_t *p_key, *p_cnt, *p_len;
+  if (W == 1) { Scratch<1> sc; sc.bind(base, pl.cap_items, pl.cap_entries); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+  else if (W == 2) { Scratch<2> sc; sc.bind(base, pl.cap_items, pl.cap_entries); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+  else { Scratch<3> sc; sc.bind(base, pl.cap_items, pl.cap_entries); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+  if (n) {
+    CUDA_TRY(cudaMemcpy(keys.data(), p_key, (size_t)n * W * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(cnt.data(), p_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(len.data(), p_len, (size_t)n, cudaMemcpyDeviceToHost));
+  }
+  t->stats[9] += (uint64_t)n * (W * 8 + 5);
+  for (uint32_t i = 0; i < n; ++i) {
+    for (uint32_t j = 0; j < len[i]; ++j) {
+      uint64_t w = keys[(size_t)i * W + j / kPrefsPerWord];
+      out->prefs.push_back((uint8_t)((w >> (kPrefBits * (j % kPrefsPerWord))) & 31u));
+    }
+    out->offsets.push_back(out->prefs.size());
+    out->counts.push_back(cnt[i]);
+  }
+  (void)nc;
+  return DTREE_OK;
+}
+
+void append_observed(const FlatTree &F, dtree_ballots *out) {
+  for (size_t i = 0; i < F.obs_counts.size(); ++i) {
+    out->prefs.insert(out->prefs.end(), F.obs_prefs.begin() + F.obs_offsets[i], F.obs_prefs.begin() + F.obs_offsets[i + 1]);
+    out->offsets.push_back(out->prefs.size());
+    out->counts.push_back(F.obs_counts[i]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *dtree_last_error(void) { return g_error.c_str(); }
+const char *dtree_version(void) { return "dtree_b200 0.1 (sm_100a)"; }
+
+int dtree_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int dtree_create(uint32_t nc, uint32_t min_depth, uint32_t max_depth, double a0, int vd, int device, dtree_t **out) {
+  if (!out) return fail(DTREE_ERR_ARG, "null output pointer");
+  *out = nullptr;
+  if (nc < 2 || nc > DTREE_MAX_CANDIDATES) return fail(DTREE_ERR_ARG, "n_candidates must be in [2, %d]", DTREE_MAX_CANDIDATES);
+  if (!(a0 >= 0.0) || !std::isfinite(a0)) return fail(DTREE_ERR_ARG, "`a0` must be >= 0.");
+  if (min_depth > max_depth || max_depth > nc)
+    return fail(DTREE_ERR_ARG, "min_depth and max_depth must satisfy: 0 <= min_depth <= max_depth <= n_candidates");
+  HostParams P;
+  P.nc = nc;
+  P.min_depth = min_depth;
+  P.max_depth = max_depth;
+  P.a0 = a0;
+  P.vd = vd != 0;
+  dtree *t = new dtree(P, device);
+  // The device is bound lazily so that a tree can be built and inspected on a host without a GPU;
+  // anything that samples resolves it (and fails loudly if there is none).
+  *out = t;
+  return DTREE_OK;
+}
+
+int dtree_destroy(dtree_t *t) {
+  if (!t) return DTREE_OK;
+  if (t->sm_count) {
+    DeviceGuard g(t->device);
+    t->d_node_base.release(); t->d_slot_count.release(); t->d_obs_cnt.release(); t->d_obs_tally0.release();
+    t->d_slot_child.release(); t->d_slot_cand.release(); t->d_obs_first.release(); t->d_obs_key.release();
+    t->d_scratch.release(); t->d_wins.release(); t->d_stats.release(); t->d_counter.release(); t->d_error.release();
+    t->d_entry_count.release(); t->d_orders.release();
+  }
+  delete t;
+  return DTREE_OK;
+}
+
+int dtree_set_min_depth(dtree_t *t, uint32_t v) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  t->tree.P.min_depth = v;  // irv_node.h:127: depth factors deliberately NOT recomputed
+  return DTREE_OK;
+}
+int dtree_set_max_depth(dtree_t *t, uint32_t v) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  if (v > t->tree.P.nc) return fail(DTREE_ERR_ARG, "max_depth must be <= n_candidates");
+  t->tree.P.max_depth = v;
+  t->tree.P.recompute_depth_factors();  // irv_node.h:134-137
+  return DTREE_OK;
+}
+int dtree_set_a0(dtree_t *t, double v) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  if (!(v >= 0.0) || !std::isfinite(v)) return fail(DTREE_ERR_ARG, "`a0` must be >= 0.");
+  t->tree.P.a0 = v;
+  return DTREE_OK;
+}
+int dtree_set_vd(dtree_t *t, int v) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  t->tree.P.vd = v != 0;
+  return DTREE_OK;
+}
+uint32_t dtree_n_candidates(const dtree_t *t) { return t->tree.P.nc; }
+uint32_t dtree_min_depth(const dtree_t *t) { return t->tree.P.min_depth; }
+uint32_t dtree_max_depth(const dtree_t *t) { return t->tree.P.max_depth; }
+double dtree_a0(const dtree_t *t) { return t->tree.P.a0; }
+int dtree_vd(const dtree_t *t) { return t->tree.P.vd ? 1 : 0; }
+uint32_t dtree_depth_factors(const dtree_t *t, double *out, uint32_t cap) {
+  const std::vector<double> &f = t->tree.P.depth_factors;
+  for (uint32_t i = 0; i < f.size() && i < cap; ++i) out[i] = f[i];
+  return (uint32_t)f.size();
+}
+
+int dtree_update(dtree_t *t, const uint8_t *prefs, const uint64_t *offsets, uint64_t n, uint64_t *n_short) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  if (n_short) *n_short = 0;
+  if (n == 0) return DTREE_OK;
+  if (!offsets || (!prefs && offsets[n] > 0)) return fail(DTREE_ERR_ARG, "null ballot buffers");
+  if (t->tree.n_observed() + n > 0xFFFFFFFFull) return fail(DTREE_ERR_STATE, "more than 2^32-1 observed ballots");
+  std::string err;
+  if (!t->tree.update(prefs, offsets, n, n_short, err)) return fail(DTREE_ERR_ARG, "%s", err.c_str());
+  return DTREE_OK;
+}
+
+int dtree_reset(dtree_t *t) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  t->tree.reset();
+  return DTREE_OK;
+}
+uint64_t dtree_n_observed(const dtree_t *t) { return t->tree.n_observed(); }
+uint64_t dtree_observed_depth_mask(const dtree_t *t) { return t->tree.depth_mask(); }
+uint64_t dtree_n_nodes(const dtree_t *t) { return t->tree.n_nodes(); }
+
+int dtree_export_nodes(const dtree_t *t, uint32_t *buf, uint64_t cap, uint64_t *needed) {
+  if (!t || !needed) return fail(DTREE_ERR_ARG, "null argument");
+  FlatTree F;
+  t->tree.flatten(F);
+  const uint32_t nc = t->tree.P.nc;
+  std::vector<uint32_t> out;
+  // prefixes by propagation in level order
+  std::vector<std::vector<uint8_t>> prefix(F.n_nodes());
+  for (uint32_t i = 0; i < F.n_nodes(); ++i) {
+    uint32_t depth = F.node_depth[i], K = nc - depth, base = F.node_base[i];
+    out.push_back(depth);
+    for (uint8_t c : prefix[i]) out.push_back(c);
+    out.push_back(K);
+    for (uint32_t j = 0; j < K; ++j) out.push_back(F.slot_cand[base + j]);
+    for (uint32_t j = 0; j <= K; ++j) out.push_back(F.slot_count[base + j]);
+    for (uint32_t j = 0; j < K; ++j) {
+      int32_t c = F.slot_child[base + j];
+      out.push_back(c >= 0);
+      if (c >= 0) {
+        prefix[c] = prefix[i];
+        prefix[c].push_back(F.slot_cand[base + j]);
+      }
+    }
+    std::vector<uint8_t>().swap(prefix[i]);
+  }
+  *needed = out.size();
+  if (buf && cap >= out.size()) std::copy(out.begin(), out.end(), buf);
+  return DTREE_OK;
+}
+
+int dtree_observed(const dtree_t *t, dtree_ballots_t **out) {
+  if (!t || !out) return fail(DTREE_ERR_ARG, "null argument");
+  FlatTree F;
+  t->tree.flatten(F);
+  dtree_ballots *b = new dtree_ballots;
+  append_observed(F, b);
+  *out = b;
+  return DTREE_OK;
+}
+
+static int bind_device(dtree_t *t) {
+  if (t->sm_count) return DTREE_OK;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(DTREE_ERR_CUDA, "no CUDA device available: libdtree_b200 has no CPU path");
+  }
+  if (t->device < 0) CUDA_TRY(cudaGetDevice(&t->device));
+  if (t->device >= n) return fail(DTREE_ERR_ARG, "device %d does not exist (%d visible)", t->device, n);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, t->device));
+  if (prop.major < 10) return fail(DTREE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", t->device, prop.major, prop.minor);
+  t->sm_count = prop.multiProcessorCount;
+  t->smem_optin = prop.sharedMemPerBlockOptin;
+  return DTREE_OK;
+}
+
+int dtree_sync_device(dtree_t *t) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  int rc = bind_device(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  return ensure_mirror(t, 0);
+}
+
+int dtree_invalidate_device(dtree_t *t) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  t->mirrored_version = ~0ull;
+  return DTREE_OK;
+}
+
+int dtree_sample_posterior(dtree_t *t, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots,
+                           uint32_t n_winners, int replace, const char *seed, size_t seed_len, uint64_t *win_counts,
+                           uint8_t *elim_orders) {
+  if (!t || !win_counts) return fail(DTREE_ERR_ARG, "null argument");
+  int rc = bind_device(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  const uint32_t nc = t->tree.P.nc;
+  CUDA_TRY(t->d_wins.reserve(kMaxCandidates));
+  CUDA_TRY(cudaMemsetAsync(t->d_wins.p, 0, kMaxCandidates * sizeof(unsigned long long), 0));
+  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = 0;
+  rc = run_posterior(t, first_election, n_elections, n_ballots, n_winners, replace, seed, seed_len, t->d_wins.p,
+                     elim_orders, 0, true);
+  if (rc) return rc;
+  unsigned long long w[kMaxCandidates];
+  CUDA_TRY(cudaMemcpy(w, t->d_wins.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  t->stats[9] += nc * 8;
+  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = w[c];
+  return DTREE_OK;
+}
+
+int dtree_sample_posterior_device(dtree_t *t, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots,
+                                  uint32_t n_winners, int replace, const char *seed, size_t seed_len,
+                                  uint64_t *d_win_counts, void *stream) {
+  if (!t || !d_win_counts) return fail(DTREE_ERR_ARG, "null argument");
+  int rc = bind_device(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  return run_posterior(t, first_election, n_elections, n_ballots, n_winners, replace, seed, seed_len,
+                       (unsigned long long *)d_win_counts, nullptr, (cudaStream_t)stream, false);
+}
+
+int dtree_sample_posterior_finish(dtree_t *t, void *stream) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  if (!t->sm_count) return DTREE_OK;
+  DeviceGuard g(t->device);
+  if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (!t->d_error.p || !t->d_stats.p) return DTREE_OK;
+  int err = 0;
+  unsigned long long st[kStatCount];
+  CUDA_TRY(cudaMemcpy(&err, t->d_error.p, sizeof err, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(st, t->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
+  if (err) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
+  t->stats[2] = st[kStatEntries];
+  t->stats[3] = st[kStatItems];
+  t->stats[4] = st[kStatGammas];
+  t->stats[5] = st[kStatBinomials];
+  t->stats[6] = st[kStatRereads];
+  t->stats[10] = st[kStatSlots];
+  t->stats[11] = st[kStatUrnItems];
+  return DTREE_OK;
+}
+
+int dtree_sample_predictive(dtree_t *t, uint32_t n_ballots, const char *seed, size_t seed_len, dtree_ballots_t **out) {
+  if (!t || !out) return fail(DTREE_ERR_ARG, "null argument");
+  *out = nullptr;
+  int rc = check_sampling_args(t, n_ballots, seed, seed_len);
+  if (rc) return rc;
+  rc = bind_device(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  dtree_ballots *b = new dtree_ballots;
+  rc = n_ballots ? run_dump(t, 0, n_ballots, seed, seed_len, b) : DTREE_OK;
+  if (rc) {
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return DTREE_OK;
+}
+
+int dtree_posterior_set(dtree_t *t, uint64_t election, uint32_t n_ballots, int replace, const char *seed,
+                        size_t seed_len, dtree_ballots_t **out) {
+  if (!t || !out) return fail(DTREE_ERR_ARG, "null argument");
+  *out = nullptr;
+  int rc = check_sampling_args(t, n_ballots, seed, seed_len);
+  if (rc) return rc;
+  if (!replace && (uint64_t)n_ballots < t->tree.n_observed())
+    return fail(DTREE_ERR_STATE, "`nBallots` must be larger than the number of ballots observed to obtain the posterior.");
+  rc = bind_device(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  dtree_ballots *b = new dtree_ballots;
+  uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->tree.n_observed();
+  rc = ensure_mirror(t, 0);
+  if (!rc && !replace) append_observed(t->flat, b);
+  if (!rc && n_sample) rc = run_dump(t, election, n_sample, seed, seed_len, b);
+  if (rc) {
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return DTREE_OK;
+}
+
+int dtree_irv(const uint8_t *prefs, const uint64_t *offsets, const uint32_t *counts, uint64_t n, uint32_t nc,
+              const char *seed, size_t seed_len, int device, uint32_t *order_out, uint32_t *tie_rounds) {
+  if (!order_out || (n && (!offsets || !counts))) return fail(DTREE_ERR_ARG, "null argument");
+  if (nc < 2 || nc > DTREE_MAX_CANDIDATES) return fail(DTREE_ERR_ARG, "n_candidates must be in [2, %d]", DTREE_MAX_CANDIDATES);
+  if (n > 0xFFFFFFF0ull) return fail(DTREE_ERR_ARG, "too many distinct ballots");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(DTREE_ERR_CUDA, "no CUDA device available: libdtree_b200 has no CPU path");
+  }
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  DeviceGuard g(device);
+  if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", device);
+  const int W = key_words_for(nc);
+  std::vector<uint64_t> keys(n * W + 1);
+  std::vector<uint8_t> lens(n + 1);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t len = offsets[i + 1] - offsets[i];
+    if (len > nc) return fail(DTREE_ERR_ARG, "ballot ranks more candidates than exist");
+    for (uint64_t j = offsets[i]; j < offsets[i + 1]; ++j)
+      if (prefs[j] >= nc) return fail(DTREE_ERR_ARG, "Invalid candidate found during social-choice evaluation.");
+    uint64_t k[kMaxKeyWords];
+    uint32_t pl = 0;
+    pack_ballot(prefs + offsets[i], (uint32_t)len, nc, false, k, &pl);
+    for (int w = 0; w < W; ++w) keys[i * W + w] = k[w];
+    lens[i] = (uint8_t)pl;
+  }
+  uint32_t cap = (uint32_t)std::max<uint64_t>(n, 1);
+  uint64_t bytes = W == 1 ? Scratch<1>::bytes(0, cap, 0) : W == 2 ? Scratch<2>::bytes(0, cap, 0) : Scratch<3>::bytes(0, cap, 0);
+  DevBuf<uint8_t> scratch, d_order;
+  DevBuf<uint32_t> d_ties;
+  auto cleanup = [&]() { scratch.release(); d_order.release(); d_ties.release(); };
+  cudaError_t e = scratch.reserve(bytes);
+  if (e == cudaSuccess) e = d_order.reserve(kMaxCandidates);
+  if (e == cudaSuccess) e = d_ties.reserve(1);
+  uint8_t *p_key = nullptr, *p_cnt = nullptr, *p_len = nullptr;
+  if (e == cudaSuccess) {
+    if (W == 1) { Scratch<1> sc; sc.bind(scratch.p, 0, cap); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+    else if (W == 2) { Scratch<2> sc; sc.bind(scratch.p, 0, cap); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+    else { Scratch<3> sc; sc.bind(scratch.p, 0, cap); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+    if (n) {
+      e = cudaMemcpy(p_key, keys.data(), n * W * 8, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMemcpy(p_cnt, counts, n * 4, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMemcpy(p_len, lens.data(), n, cudaMemcpyHostToDevice);
+    }
+  }
+  if (e == cudaSuccess) {
+    IrvArgs ia;
+    ia.nc = nc;
+    ia.n_entries = (uint32_t)n;
+    ia.seed = hash_seed(seed, seed_len);
+    ia.scratch = scratch.p;
+    ia.cap_entries = cap;
+    ia.order_out = d_order.p;
+    ia.tie_rounds_out = d_ties.p;
+    e = W == 1 ? launch_irv_only<1>(ia, 0) : W == 2 ? launch_irv_only<2>(ia, 0) : launch_irv_only<3>(ia, 0);
+  }
+  uint8_t order8[kMaxCandidates];
+  uint32_t ties = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(order8, d_order.p, nc, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(&ties, d_ties.p, 4, cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(DTREE_ERR_CUDA, "dtree_irv: %s", cudaGetErrorString(e));
+  for (uint32_t c = 0; c < nc; ++c) order_out[c] = order8[c];
+  if (tie_rounds) *tie_rounds = ties;
+  return DTREE_OK;
+}
+
+uint64_t dtree_ballots_size(const dtree_ballots_t *b) { return b->counts.size(); }
+uint64_t dtree_ballots_total_prefs(const dtree_ballots_t *b) { return b->prefs.size(); }
+int dtree_ballots_export(const dtree_ballots_t *b, uint8_t *prefs, uint64_t *offsets, uint32_t *counts) {
+  if (!b || !offsets) return fail(DTREE_ERR_ARG, "null argument");
+  if (prefs && !b->prefs.empty()) memcpy(prefs, b->prefs.data(), b->prefs.size());
+  memcpy(offsets, b->offsets.data(), b->offsets.size() * sizeof(uint64_t));
+  if (counts && !b->counts.empty()) memcpy(counts, b->counts.data(), b->counts.size() * sizeof(uint32_t));
+  return DTREE_OK;
+}
+void dtree_ballots_free(dtree_ballots_t *b) { delete b; }
+
+int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user) {
+  if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  t->should_abort = should_abort;
+  t->abort_user = user;
+  return DTREE_OK;
+}
+
+int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
+  if (!t || !key) return fail(DTREE_ERR_ARG, "null argument");
+  if (!strcmp(key, "block_threads")) t->block_threads = (int)value;
+  else if (!strcmp(key, "blocks_per_sm")) t->blocks_per_sm = (int)value;
+  else if (!strcmp(key, "urn_max")) {
+    if (value < 0 || value > 8) return fail(DTREE_ERR_ARG, "urn_max must be in [0, 8]");
+    t->urn_max = (uint32_t)value;
+  } else return fail(DTREE_ERR_ARG, "unknown tuning key '%s'", key);
+  return DTREE_OK;
+}
+
+int dtree_last_stats(const dtree_t *t, uint64_t *out, uint32_t cap) {
+  if (!t || !out) return fail(DTREE_ERR_ARG, "null argument");
+  for (uint32_t i = 0; i < cap && i < 16; ++i) out[i] = t->stats[i];
+  return DTREE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// host_tree.cpp — see host_tree.h.
+#include "host_tree.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace dtb {
+
+// irv_node.cpp:13-25: F[max_depth-1] = 1; F[d-1] = F[d] * (#outcomes of a node at depth d).
+void HostParams::recompute_depth_factors() {
+  depth_factors.assign(max_depth, 0.0);
+  double f = 1.0;
+  for (int d = (int)max_depth - 1; d >= 0; --d) {
+    depth_factors[d] = f;
+    f *= (double)(nc - (uint32_t)d + ((uint32_t)d >= min_depth ? 1u : 0u));
+  }
+}
+
+HostTree::HostTree(const HostParams &p) : P(p) {
+  P.recompute_depth_factors();
+  reset();
+}
+
+void HostTree::reset() {
+  depth_.clear();
+  base_.clear();
+  counts_.clear();
+  child_.clear();
+  n_observed_ = 0;
+  depth_mask_ = 0;
+  new_node(0);
+  ++version_;
+}
+
+int32_t HostTree::new_node(uint32_t depth) {
+  uint32_t K = P.nc - depth;
+  depth_.push_back((uint8_t)depth);
+  base_.push_back(counts_.size());
+  counts_.resize(counts_.size() + K + 1, 0u);
+  child_.resize(child_.size() + K + 1, -1);
+  return (int32_t)depth_.size() - 1;
+}
+
+// IRVNode::update, irv_node.cpp:176-221, iteratively. `path` starts as the identity and
+// receives the reference's swaps, which fixes the slot <-> candidate mapping.
+void HostTree::insert(const uint8_t *b, uint32_t len) {
+  uint8_t path[kMaxCandidates];
+  for (uint32_t i = 0; i < P.nc; ++i) path[i] = (uint8_t)i;
+  int32_t cur = 0;
+  for (;;) {
+    uint32_t depth = depth_[cur], K = P.nc - depth;
+    uint64_t base = base_[cur];
+    if (depth == len) {  // :191-194 the ballot stops here
+      counts_[base + K] += 1;
+      return;
+    }
+    uint32_t i = depth;
+    while (path[i] != b[depth]) ++i;  // :203-205
+    uint32_t slot = i - depth;
+    counts_[base + slot] += 1;
+    if (K == 2) return;  // :210 the last two levels are never materialised
+    int32_t c = child_[base + slot];
+    if (c < 0) {
+      c = new_node(depth + 1);
+      child_[base + slot] = c;
+    }
+    std::swap(path[depth], path[i]);
+    cur = c;
+  }
+}
+
+bool HostTree::update(const uint8_t *prefs, const uint64_t *offsets, uint64_t n, uint64_t *n_short,
+                      std::string &err) {
+  uint64_t shorts = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (offsets[i + 1] < offsets[i]) { err = "ballot offsets must be non-decreasing"; return false; }
+    uint64_t len = offsets[i + 1] - offsets[i];
+    if (len > P.nc) { err = "ballot ranks more candidates than exist"; return false; }
+    uint32_t seen = 0;
+    for (uint64_t j = offsets[i]; j < offsets[i + 1]; ++j) {
+      uint32_t c = prefs[j];
+      if (c >= P.nc) { err = "Unknown candidate encountered in ballot!"; return false; }  // R_tree.cpp:30-31
+      if (seen >> c & 1u) { err = "ballot ranks a candidate more than once"; return false; }
+      seen |= 1u << c;
+    }
+    if (len > 0 && len < P.min_depth) ++shorts;  // R_tree.cpp:139
+  }
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t len = (uint32_t)(offsets[i + 1] - offsets[i]);
+    insert(prefs + offsets[i], len);
+    n_observed_ += 1;            // R_tree.cpp:149
+    depth_mask_ |= 1ull << len;  // R_tree.cpp:151
+  }
+  if (n_short) *n_short = shorts;
+  if (n) ++version_;
+  return true;
+}
+
+void FlatTree::node_prefix(uint32_t node, std::vector<uint8_t> &out) const {
+  out.resize(node_depth[node]);
+  uint32_t cur = node;
+  while (node_depth[cur] > 0) {
+    uint32_t ps = node_parent_slot[cur];
+    out[node_depth[cur] - 1] = slot_cand[ps];
+    // parent = the node owning slot ps: last node whose base <= ps
+    uint32_t parent = (uint32_t)(std::upper_bound(node_base.begin(), node_base.end(), ps) - node_base.begin()) - 1;
+    cur = parent;
+  }
+}
+
+// Breadth-first renumbering: nodes of one depth contiguous, siblings adjacent, so that a
+// frontier processed in order reads slot_count with unit stride.
+void HostTree::flatten(FlatTree &F) const {
+  const uint32_t nc = P.nc;
+  F = FlatTree();
+  struct QItem { int32_t arena; uint32_t parent_slot; uint8_t path[kMaxCandidates]; };
+  std::vector<QItem> cur(1), next;
+  cur[0].arena = 0;
+  cur[0].parent_slot = UINT32_MAX;
+  for (uint32_t i = 0; i < nc; ++i) cur[0].path[i] = (uint8_t)i;
+  F.node_base.push_back(0);
+  std::vector<uint8_t> prefix;
+  uint32_t depth = 0;
+  while (!cur.empty()) {
+    F.level_first.push_back(F.n_nodes());
+    next.clear();
+    uint32_t K = nc - depth;
+    // ids of this level's children are assigned in order of appearance
+    uint32_t next_id = F.n_nodes() + (uint32_t)cur.size();
+    for (const QItem &q : cur) {
+      uint64_t base = base_[q.arena];
+      uint32_t fbase = (uint32_t)F.slot_count.size();
+      for (uint32_t j = 0; j <= K; ++j) {
+        F.slot_count.push_back(counts_[base + j]);
+        F.slot_cand.push_back(j < K ? q.path[depth + j] : (uint8_t)0xFF);
+        int32_t c = j < K ? child_[base + j] : -1;
+        if (c >= 0) {
+          QItem nq;
+          nq.arena = c;
+          nq.parent_slot = fbase + j;
+          std::memcpy(nq.path, q.path, nc);
+          std::swap(nq.path[depth], nq.path[depth + j]);
+          next.push_back(nq);
+          F.slot_child.push_back((int32_t)next_id++);
+        } else {
+          F.slot_child.push_back(-1);
+        }
+      }
+      F.node_depth.push_back((uint8_t)depth);
+      F.node_parent_slot.push_back(q.parent_slot);
+      F.node_base.push_back((uint32_t)F.slot_count.size());
+      // Observed ballots that END at this node: the stop slot, and at K == 2 (never expanded,
+      // irv_node.cpp:210) also the two child slots, which stand for prefix+cand (with or
+      // without the implied last preference).
+      uint32_t stop = counts_[base + K];
+      bool leafish = (K == 2);
+      if (stop || (leafish && (counts_[base] || counts_[base + 1]))) {
+        prefix.assign(q.path, q.path + depth);
+        if (stop) {
+          F.obs_prefs.insert(F.obs_prefs.end(), prefix.begin(), prefix.end());
+          F.obs_offsets.push_back(F.obs_prefs.size());
+          F.obs_counts.push_back(stop);
+        }
+        if (leafish)
+          for (uint32_t j = 0; j < 2; ++j)
+            if (counts_[base + j]) {
+              F.obs_prefs.insert(F.obs_prefs.end(), prefix.begin(), prefix.end());
+              F.obs_prefs.push_back(q.path[depth + j]);
+              F.obs_offsets.push_back(F.obs_prefs.size());
+              F.obs_counts.push_back(counts_[base + j]);
+            }
+      }
+    }
+    cur.swap(next);
+    ++depth;
+  }
+  F.level_first.push_back(F.n_nodes());
+  F.obs_offsets.insert(F.obs_offsets.begin(), 0);
+}
+
+// FNV-1a over the seed bytes, then a splitmix64 finaliser: same string => same 64-bit key,
+// which is all the reference's seed strings promise (R/dtree.R:682-684, test-determinism.R).
+uint64_t hash_seed(const char *seed, size_t len) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (size_t i = 0; i < len; ++i) {
+    h ^= (uint8_t)seed[i];
+    h *= 0x100000001b3ull;
+  }
+  h += 0x9e3779b97f4a7c15ull;
+  h = (h ^ (h >> 30)) * 0xbf58476d1ce4e5b9ull;
+  h = (h ^ (h >> 27)) * 0x94d049bb133111ebull;
+  return h ^ (h >> 31);
+}
+
+}  // namespace dtb

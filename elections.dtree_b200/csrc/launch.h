@@ -1,0 +1,41 @@
+// launch.h — host-callable entry points of the kernels, one translation unit per key width W.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "simulate.cuh"
+
+namespace dtb {
+
+struct LaunchCfg {
+  int block;        // threads per block: one of kBlockSizes
+  bool log_gamma;   // small-alpha regime (Gamma variates carried as logarithms)
+  int grid;
+  cudaStream_t stream;
+};
+
+constexpr int kBlockSizes[] = {32, 64, 128, 256};
+constexpr int kNumBlockSizes = 4;
+
+inline size_t simulate_smem_bytes(uint32_t nc, int block) { return (size_t)block * ((nc + 1u) | 1u) * sizeof(float); }
+
+// Launches simulate_kernel<W, block, log>. Returns cudaErrorInvalidValue for an unsupported block size.
+template <int W>
+cudaError_t launch_simulate(const SimArgs &a, const LaunchCfg &cfg);
+// Resident blocks per SM for that instantiation (occupancy API).
+template <int W>
+int simulate_blocks_per_sm(uint32_t nc, int block, bool log_gamma);
+
+// Stand-alone IRV over entries already placed in block 0's scratch (dtree_irv).
+struct IrvArgs {
+  uint32_t nc;
+  uint32_t n_entries;
+  uint64_t seed;
+  uint8_t *scratch;
+  uint32_t cap_entries;
+  uint8_t *order_out;       // [nc] device
+  uint32_t *tie_rounds_out; // [1] device
+};
+template <int W>
+cudaError_t launch_irv_only(const IrvArgs &a, cudaStream_t stream);
+
+}  // namespace dtb

@@ -1,0 +1,29 @@
+/* dtree_b200_debug.h — test hooks exported by libdtree_b200.so next to the product ABI
+ * (include/dtree_b200.h). They expose the device random-variate generators on their own so that
+ * tests/ can check them distributionally (the reference's counterparts are libstdc++'s
+ * std::gamma_distribution / std::binomial_distribution, called from distributions.cpp:45-46,63-64).
+ * Not part of the drop-in boundary. */
+#ifndef DTREE_B200_DEBUG_H
+#define DTREE_B200_DEBUG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Philox4x32-10 of one counter block, evaluated on the host (on_device = 0) or by a one-thread
+ * kernel (on_device = 1): the two must agree and match the published known-answer vectors. */
+int dtree_debug_philox(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4], int on_device);
+/* 64-bit seed derived from a seed string (what every sampling call does with `seed`). */
+uint64_t dtree_debug_hash_seed(const char *seed, size_t seed_len);
+/* n independent Gamma(alpha, 1) variates (log_space = 0) or their logarithms (log_space = 1). */
+int dtree_debug_gamma(double alpha, int log_space, uint64_t seed, uint32_t n, float *out, int device);
+/* n independent Binomial(n_trials, p) variates, 0 <= p <= 1. */
+int dtree_debug_binomial(uint32_t n_trials, double p, uint64_t seed, uint32_t n, uint32_t *out, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -15,7 +15,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def load_pkg():
+def load_pkg():  # same loader as __graft_entry__.load_pkg
     """Import the package directory `elections.dtree_b200/` (its name is not a Python identifier)."""
     name = "elections_dtree_b200"
     if name in sys.modules:

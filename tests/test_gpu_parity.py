@@ -1,0 +1,498 @@
+"""GPU parity tests: everything calls the CUDA path through the C ABI (ctypes) and is checked
+against the CPU oracle (oracle/, pinned to the reference by tests/test_oracle_pin.py).
+
+ * bit-exact: IRV elimination orders on identical ballots (Wakehurst golden vector, oracle-sampled
+   elections, and the kernel's own elections re-run by the oracle), win counts over election ranges;
+ * distributional (fixed seeds, tolerances written at each assert): Gamma / binomial generators,
+   Dirichlet-tree marginals vs closed form and vs the oracle, ballot-type chi-squares, posterior win
+   probabilities within binomial Monte-Carlo error of the oracle's.
+"""
+import ctypes as C
+import warnings
+
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L(pkg):
+    lib = pkg._native.lib()
+    if lib.dtree_device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests cannot run (there is no CPU fallback)")
+    return lib
+
+
+def names(pkg, nc):
+    return pkg.workloads.candidate_names(nc)
+
+
+def make_pair(pkg, port, nc, mn, mx, a0, vd, prefs=None, offsets=None):
+    t = pkg.dirichlet_tree(names(pkg, nc), mn, mx, a0, vd, device=0)
+    o = port.tree(nc, mn, mx, a0, vd)
+    if prefs is not None:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t.update_indices(prefs, offsets)
+        o.update((prefs, offsets))
+    return t, o
+
+
+def type_counts(prefs, offsets, counts):
+    d = {}
+    for b, c in zip(oracle.csr_to_ballots(prefs, offsets), counts):
+        d[b] = d.get(b, 0) + int(c)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# generators
+# ------------------------------------------------------------------------------------------------
+def test_philox_device_matches_host_and_known_answers(L):
+    rng = np.random.default_rng(0)
+    cases = [([0, 0, 0, 0], [0, 0]), ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])]
+    cases += [(rng.integers(0, 2**32, 4).tolist(), rng.integers(0, 2**32, 2).tolist()) for _ in range(20)]
+    for ctr, key in cases:
+        h, d = (C.c_uint32 * 4)(), (C.c_uint32 * 4)()
+        assert L.dtree_debug_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), h, 0) == 0
+        assert L.dtree_debug_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), d, 1) == 0
+        assert list(h) == list(d)
+    assert list(d) != [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("alpha,log_space", [(1.0, 0), (1.0, 1), (2.5, 0), (30.0, 0), (1e4, 0), (3e6, 0), (0.3, 1),
+                                             (0.3, 0), (0.02, 1), (7.0, 1), (1.5, 0), (100.5, 1)])
+def test_gamma_variates_match_the_gamma_law(L, alpha, log_space):
+    """Counterpart of std::gamma_distribution in distributions.cpp:63-64 (KS p > 1e-4; mean and
+    variance within 5 standard errors)."""
+    n = 200_000
+    out = np.zeros(n, dtype=np.float32)
+    assert L.dtree_debug_gamma(alpha, log_space, 1234 + int(alpha * 10), n, out.ctypes.data_as(C.POINTER(C.c_float)), 0) == 0
+    x = out.astype(np.float64)
+    if log_space:
+        # log of a Gamma variate: compare on the log scale with the exact law of log G
+        cdf = lambda v: stats.gamma.cdf(np.exp(v), alpha)
+        assert stats.kstest(x, cdf).pvalue > 1e-4
+        x = np.exp(x)
+    else:
+        assert np.all(x > 0) or alpha < 1
+        assert stats.kstest(x, lambda v: stats.gamma.cdf(v, alpha)).pvalue > 1e-4
+    se_mean = np.sqrt(alpha / n)
+    assert abs(x.mean() - alpha) < 5 * se_mean + 1e-6 * alpha
+    var_of_var = (6 * alpha + 2 * alpha * alpha) / n  # Var of sample variance ~ (mu4 - sigma^4)/n
+    assert abs(x.var() - alpha) < 5 * np.sqrt(var_of_var) + 1e-5 * alpha
+
+
+def test_log_gamma_carries_tiny_shapes(L):
+    """a0 = 1e-4 (config C5): Gamma(a) underflows in double for 93% of draws, so the
+    reference falls back to a one-hot; the log-space variate must follow log G exactly instead:
+    P(log G <= t) = P(G <= e^t) even at e^t ~ 1e-300 and below."""
+    alpha, n = 1e-4, 200_000
+    out = np.zeros(n, dtype=np.float32)
+    assert L.dtree_debug_gamma(alpha, 1, 99, n, out.ctypes.data_as(C.POINTER(C.c_float)), 0) == 0
+    x = out.astype(np.float64)
+    assert np.all(np.isfinite(x))
+    # for tiny alpha, G ~ U^(1/alpha) so -alpha*log G ~ Exp(1) to O(alpha)
+    assert stats.kstest(-alpha * x, "expon").pvalue > 1e-4
+
+
+@pytest.mark.parametrize("n_trials,p", [(1, 0.5), (10, 0.3), (50, 0.5), (1000, 0.001), (1000, 0.3), (100, 0.97),
+                                        (20, 0.5), (40, 0.25), (10**6, 0.4), (10**6, 9.9e-6), (10**6, 1.2e-5),
+                                        (4_000_000_000, 0.5), (3_000_000_000, 1e-9), (12345, 0.9991), (37, 0.0),
+                                        (37, 1.0), (200, 0.05), (200, 0.06)])
+def test_binomial_variates_match_the_binomial_law(L, n_trials, p):
+    """Counterpart of std::binomial_distribution in distributions.cpp:45-46: chi-square against the exact pmf
+    (p > 1e-4) and mean within 5 standard errors."""
+    n = 200_000
+    out = np.zeros(n, dtype=np.uint32)
+    assert L.dtree_debug_binomial(n_trials, p, 777 + n_trials % 1000, n, out.ctypes.data_as(C.POINTER(C.c_uint32)), 0) == 0
+    x = out.astype(np.float64)
+    assert x.min() >= 0 and x.max() <= n_trials
+    if p in (0.0, 1.0):
+        assert np.all(x == n_trials * p)
+        return
+    mean, sd = n_trials * p, np.sqrt(n_trials * p * (1 - p))
+    assert abs(x.mean() - mean) < 5 * sd / np.sqrt(n) + 1e-7 * mean
+    assert abs(x.var() - sd * sd) < 0.03 * sd * sd + 1e-9
+    # chi-square over ~40 equiprobable-ish bins of the support
+    qs = np.unique(stats.binom.ppf(np.linspace(0.0005, 0.9995, 41), n_trials, p))
+    edges = np.concatenate([[-1], qs, [n_trials]])
+    edges = np.unique(edges)
+    exp = np.diff(stats.binom.cdf(edges, n_trials, p)) * n
+    obs = np.array([np.sum((x > lo) & (x <= hi)) for lo, hi in zip(edges[:-1], edges[1:])], dtype=np.float64)
+    keep = exp > 5
+    obs = np.append(obs[keep], obs[~keep].sum())
+    exp = np.append(exp[keep], exp[~keep].sum())
+    if exp[-1] < 1e-9:
+        obs, exp = obs[:-1], exp[:-1]
+    chi2 = ((obs - exp) ** 2 / np.maximum(exp, 1e-12)).sum()
+    assert stats.chi2.sf(chi2, max(len(exp) - 1, 1)) > 1e-4, (chi2, len(exp))
+
+
+# ------------------------------------------------------------------------------------------------
+# IRV, bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_irv_wakehurst_golden_vector(pkg, L, wakehurst):
+    """tests/testthat/test-socialchoice.R:11-23 through the host API and dtree_irv."""
+    cands = wakehurst["candidates"]
+    ballots = [[cands[i] for i in b] for b in wakehurst["ballots"]]
+    out = pkg.social_choice(ballots, "irv", counts=wakehurst["counts"], candidates=cands)
+    assert out["winners"] == [wakehurst["irv_winner"]]
+    assert out["elimination_order"] == wakehurst["irv_elimination_order"]
+    assert pkg.social_choice([b[:1] for b in ballots], "plurality", counts=wakehurst["counts"],
+                             candidates=cands) == [wakehurst["plurality_winner"]]
+
+
+@pytest.mark.parametrize("nc", [2, 3, 4, 6, 10, 13, 14, 20, 26, 32])
+def test_irv_bit_exact_on_random_elections(pkg, L, port, nc):
+    """dtree_irv == socialChoiceIRV (irv_ballot.cpp:42-138) on identical ballots. Tie-free elections must
+    match exactly; with ties the order must be one the reference rule allows (its tie-break consumes
+    mt19937 draws we do not reproduce)."""
+    rng = np.random.default_rng(nc)
+    exact = 0
+    for trial in range(40):
+        n = int(rng.integers(1, 400 if nc <= 20 else 3000))
+        pmf = rng.random(nc + 1) + 0.01
+        prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, float(rng.random()), n, 1000 * nc + trial, pmf)
+        counts = rng.integers(1, 1_000_000 if trial % 2 else 5, n).astype(np.uint32)
+        order, ties = pkg.irv_indices(prefs, offsets, counts, nc, "s%d" % trial, 0)
+        ok, oties = port.irv_check_order((prefs, offsets), counts, nc, order)
+        assert ok and oties == ties
+        if ties == 0:
+            assert order.tolist() == port.irv((prefs, offsets), counts, nc, "whatever").tolist()
+            exact += 1
+    assert exact >= 5
+
+
+def test_irv_bit_exact_on_reference_sampled_elections(pkg, L, port):
+    """Elections drawn by the oracle's posteriorSet, decided by both sides."""
+    nc = 8
+    prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.4, 500, 5, [1, 3, 2, 2, 2, 1, 1, 1, 6])
+    o = port.tree(nc, 0, nc, 1.0, False)
+    o.update((prefs, offsets))
+    exact = 0
+    for es in range(25):
+        p, off, cnt = o.posterior_set(20_000, False, es)
+        order, ties = pkg.irv_indices(p, off, cnt, nc, "x", 0)
+        ok, _ = port.irv_check_order((p, off), cnt, nc, order)
+        assert ok
+        if ties == 0:
+            assert order.tolist() == port.irv((p, off), cnt, nc, "y").tolist()
+            exact += 1
+    assert exact >= 20
+
+
+def test_irv_tie_break_is_uniform(pkg, L):
+    """Three candidates with equal tallies: each is eliminated first about a third of the time
+    (irv_ballot.cpp:100-102: uniform among the tied). 600 seeds, 5 sigma."""
+    prefs, offsets = np.array([0, 1, 2], dtype=np.uint8), np.array([0, 1, 2, 3], dtype=np.uint64)
+    first = np.zeros(3)
+    for s in range(600):
+        order, ties = pkg.irv_indices(prefs, offsets, [5, 5, 5], 3, "tie%d" % s, 0)
+        assert ties >= 1
+        first[order[0]] += 1
+    assert np.all(np.abs(first - 200) < 5 * np.sqrt(600 * (1 / 3) * (2 / 3)))
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler: known answers and invariants
+# ------------------------------------------------------------------------------------------------
+def test_bootstrap_known_answer(pkg, L):
+    """tests/testthat/test-minmaxdepth.R:1-27"""
+    t = pkg.dirtree(list("ABCDE"), a0=0.0, min_depth=0, max_depth=3, vd=False)
+    pkg.update(t, [["C", "B", "A", "D", "E"]])
+    for s in range(5):
+        assert pkg.sample_predictive(t, 1, seed="k%d" % s) == [(("C", "B", "A"), 1)]
+    assert pkg.sample_predictive(t, 1000, seed="k") == [(("C", "B", "A"), 1000)]
+
+
+def test_sampled_lengths_and_totals(pkg, L):
+    """tests/testthat/test-minmaxdepth.R:29-59, test-sampling.R:1-19, src/test-distributions.cpp:11-43"""
+    t = pkg.dirtree(list("ABCDEFGHIJ"), a0=1.0, min_depth=2, max_depth=8)
+    s = pkg.sample_predictive(t, 1000, seed="len")
+    assert sum(c for _, c in s) == 1000 and all(2 <= len(b) <= 8 for b, _ in s)
+    assert all(len(set(b)) == len(b) for b, _ in s)
+    t = pkg.dirtree(list("ABCDEFGHIJ"), a0=1.0, min_depth=3)
+    init = pkg.sample_predictive(t, 1000, seed="init")
+    pkg.update(t, [list(b) for b, _ in init], counts=[c for _, c in init])
+    t.a0 = 0
+    t.max_depth = 7
+    s = pkg.sample_predictive(t, 1000, seed="again")
+    assert sum(c for _, c in s) == 1000 and all(3 <= len(b) <= 7 for b, _ in s)
+    for n in (1, 2, 7, 8, 9, 33, 100_000):  # across the urn / Gamma switch
+        for nc, mn, mx in ((4, 0, 4), (13, 1, 13), (20, 0, 5), (30, 2, 30)):
+            t = pkg.dirtree(names(pkg, nc), min_depth=mn, max_depth=mx, a0=0.7)
+            p, off, cnt = t.sample_predictive_indices(n, seed="n%d" % n)
+            lens = np.diff(off.astype(np.int64))
+            assert int(cnt.sum()) == n and lens.min() >= mn and lens.max() <= min(mx, nc - 1)
+            assert len(type_counts(p, off, cnt)) == len(cnt)  # every ballot type is emitted once
+
+
+def test_determinism_and_range_splitting(pkg, L):
+    """tests/testthat/test-determinism.R:5-42, and the property the multi-GPU sharding rests on:
+    any split of [0, n) into ranges gives bit-identical totals and per-election orders."""
+    nc = 10
+    prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.3, 300, 9, None)
+    t = pkg.dirichlet_tree(names(pkg, nc), 0, nc, 1.0, False, device=0)
+    t.update_indices(prefs, offsets)
+    pkg.set_seed(1)
+    a = pkg.sample_posterior(t, 100, 1000)
+    s1 = pkg.sample_predictive(t, 1000)
+    pkg.set_seed(1)
+    assert pkg.sample_posterior(t, 100, 1000) == a and pkg.sample_predictive(t, 1000) == s1
+    w, orders = t.sample_posterior_counts(300, 2000, seed="SPLIT", return_orders=True)
+    acc = np.zeros(nc, dtype=np.uint64)
+    parts = []
+    for lo, hi in ((0, 1), (1, 38), (38, 150), (150, 300)):
+        ww, oo = t.sample_posterior_counts(hi - lo, 2000, seed="SPLIT", first_election=lo, return_orders=True)
+        acc += ww
+        parts.append(oo)
+    assert acc.tolist() == w.tolist() and np.array_equal(np.vstack(parts), orders)
+    for bt in (32, 64, 128, 256):  # the launch shape must not matter either
+        t.tune(block_threads=bt)
+        w2, o2 = t.sample_posterior_counts(300, 2000, seed="SPLIT", return_orders=True)
+        assert w2.tolist() == w.tolist() and np.array_equal(o2, orders)
+    t.tune(block_threads=0)
+    assert t.sample_posterior_counts(300, 2000, seed="OTHER").tolist() != w.tolist()
+
+
+@pytest.mark.parametrize("nc,mn,mx,a0,vd,n_obs,n_ballots,replace", [
+    (4, 0, 3, 1.0, False, 1000, 10_000, False), (6, 0, 5, 1.0, False, 300, 3000, False),
+    (8, 7, 7, 0.01, True, 200, 5000, False), (10, 0, 10, 1.0, False, 2000, 20_000, False),
+    (5, 0, 5, 0.0, False, 50, 500, False), (7, 2, 4, 3.0, False, 100, 1000, True),
+    (16, 0, 16, 1.0, False, 400, 4000, False), (27, 1, 27, 0.5, True, 300, 2000, False)])
+def test_in_kernel_irv_bit_exact_vs_oracle_on_the_kernels_own_elections(pkg, L, port, nc, mn, mx, a0, vd, n_obs,
+                                                                        n_ballots, replace):
+    """sample_posterior's elimination orders vs socialChoiceIRV run by the oracle on exactly the ballots the
+    kernel drew (dtree_posterior_set re-materialises election e). Covers the observed-ballot table, all
+    key widths, a0 = 0 and the vd option."""
+    pmf = np.ones(nc + 1)
+    pmf[:mn] = 0
+    prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.3, n_obs, nc + 50, pmf)
+    t, o = make_pair(pkg, port, nc, mn, mx, a0, vd, prefs, offsets)
+    n_el = 24
+    wins, orders = t.sample_posterior_counts(n_el, n_ballots, replace=replace, seed="OWN", return_orders=True)
+    assert int(wins.sum()) == n_el
+    recount = np.zeros(nc, dtype=np.int64)
+    exact = 0
+    for e in range(n_el):
+        p, off, cnt = t.posterior_set_indices(e, n_ballots, replace, "OWN")
+        assert int(cnt.sum()) == n_ballots
+        ok, ties = port.irv_check_order((p, off), cnt, nc, orders[e].astype(np.uint32))
+        assert ok, (e, orders[e])
+        if ties == 0:
+            assert port.irv((p, off), cnt, nc, "z").tolist() == orders[e].tolist()
+            exact += 1
+        recount[orders[e][-1]] += 1
+    assert recount.tolist() == wins.tolist()
+    assert exact >= n_el // 2 or a0 == 0.0 or nc > 10
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler: distributions
+# ------------------------------------------------------------------------------------------------
+def test_root_split_is_dirichlet_multinomial(pkg, L):
+    """First-preference tallies of sample(n) are DirMult(n, as_root + a0): mean n a_i/A, variance
+    n (a_i/A)(1 - a_i/A)(A + n)/(A + 1). 4000 draws, 5 standard errors."""
+    nc, n, draws = 5, 1000, 4000
+    prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.6, 40, 3, [1, 1, 1, 1, 1, 3])
+    t = pkg.dirichlet_tree(names(pkg, nc), 0, nc, 1.5, False, device=0)
+    t.update_indices(prefs, offsets)
+    dump = oracle.parse_node_dump(t.export_nodes())
+    cands, counts, _ = dump[()]
+    alpha = np.array(counts, dtype=np.float64) + 1.5  # nc candidates + stop
+    A = alpha.sum()
+    tallies = np.zeros((draws, nc + 1))
+    for e in range(draws):
+        p, off, cnt = t.posterior_set_indices(e, n, True, "ROOT")
+        for b, c in zip(oracle.csr_to_ballots(p, off), cnt):
+            tallies[e, cands.index(b[0]) if b else nc] += c
+    assert np.all(tallies.sum(1) == n)
+    mean = n * alpha / A
+    var = n * (alpha / A) * (1 - alpha / A) * (A + n) / (A + 1)
+    assert np.all(np.abs(tallies.mean(0) - mean) < 5 * np.sqrt(var / draws))
+    assert np.all(np.abs(tallies.var(0) - var) < 0.15 * var)  # ~6 sigma of a sample variance at 4000 draws
+
+
+def test_small_count_urn_matches_gamma_path(pkg, L):
+    """The Polya-urn shortcut (counts <= urn_max) and the Gamma/binomial path must sample the same law:
+    ballot-type frequencies of 30000 predictive draws of n=6 ballots, two-sample chi-square p > 1e-4."""
+    nc = 4
+    prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.5, 30, 8, [1, 2, 2, 2, 4])
+    freq = []
+    for urn in (8, 0):
+        t = pkg.dirichlet_tree(names(pkg, nc), 0, nc, 0.8, False, device=0).tune(urn_max=urn)
+        t.update_indices(prefs, offsets)
+        d = {}
+        for e in range(30000):
+            for b, c in type_counts(*t.posterior_set_indices(e, 6, True, "URN")).items():
+                d[b] = d.get(b, 0) + c
+        freq.append(d)
+    keys = sorted(set(freq[0]) | set(freq[1]))
+    tab = np.array([[f.get(k, 0) for k in keys] for f in freq], dtype=np.float64)
+    tab = tab[:, tab.sum(0) >= 10]
+    assert stats.chi2_contingency(tab)[1] > 1e-4
+
+
+@pytest.mark.parametrize("nc,mn,mx,a0,vd,n_obs", [(4, 0, 4, 1.0, False, 30), (5, 2, 4, 0.3, False, 20),
+                                                  (4, 3, 3, 2.0, True, 10), (6, 0, 3, 5.0, False, 100)])
+def test_ballot_type_frequencies_match_the_oracle(pkg, L, port, nc, mn, mx, a0, vd, n_obs):
+    """Chi-square on sampled ballot-type frequencies, GPU vs oracle: 3000 elections of 200 ballots each side
+    (two-sample, p > 1e-4), plus the per-election spread of the commonest type (variance ratio in [0.8, 1.25])."""
+    pmf = np.ones(nc + 1)
+    pmf[:mn] = 0
+    prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.4, n_obs, nc, pmf)
+    t, o = make_pair(pkg, port, nc, mn, mx, a0, vd, prefs, offsets)
+    n_el, n = 3000, 200
+    tot = [{}, {}]
+    per = [[], []]
+    for e in range(n_el):
+        for side, tc in ((0, type_counts(*t.posterior_set_indices(e, n, True, "CHI"))),
+                         (1, type_counts(*o.posterior_set(n, True, e)))):
+            for b, c in tc.items():
+                tot[side][b] = tot[side].get(b, 0) + c
+            per[side].append(tc)
+    keys = sorted(set(tot[0]) | set(tot[1]))
+    tab = np.array([[f.get(k, 0) for k in keys] for f in tot], dtype=np.float64)
+    assert tab[0].sum() == tab[1].sum() == n_el * n
+    top = keys[int(np.argmax(tab.sum(0)))]
+    tab = tab[:, tab.sum(0) >= 20]
+    # counts within an election are overdispersed (Dirichlet mixing), so the plain chi-square is too
+    # strict; scale it by the overdispersion estimated from the oracle's own two halves
+    va = np.var([d.get(top, 0) for d in per[0]])
+    vb = np.var([d.get(top, 0) for d in per[1]])
+    assert 0.8 < va / vb < 1.25
+    half = np.array([[sum(d.get(k, 0) for d in per[1][h::2]) for k in keys] for h in (0, 1)], dtype=np.float64)
+    half = half[:, half.sum(0) >= 20]
+    base = stats.chi2_contingency(half)[0] / max(half.shape[1] - 1, 1)
+    chi2 = stats.chi2_contingency(tab)[0] / max(tab.shape[1] - 1, 1)
+    assert chi2 < max(2.0 * base, 2.0), (chi2, base)
+
+
+def test_vd_prior_is_uniform_over_ballot_types(pkg, L):
+    """vd=TRUE on an empty tree is a flat Dirichlet over complete ballots (README / dtree paper): with
+    min_depth = max_depth every ballot type has the same mean frequency. 4 candidates -> 24 types,
+    2000 elections x 240 ballots; Dirichlet(1,...,1)-multinomial variance, 5 sigma."""
+    nc = 4
+    t = pkg.dirichlet_tree(names(pkg, nc), 3, 3, 1.0, True, device=0)
+    tot = {}
+    n_el, n = 2000, 240
+    for e in range(n_el):
+        for b, c in type_counts(*t.posterior_set_indices(e, n, True, "VD")).items():
+            assert len(b) == 3
+            tot[b] = tot.get(b, 0) + c
+    assert len(tot) == 24
+    x = np.array(list(tot.values()), dtype=np.float64)
+    A, p = 24.0, 1 / 24.0
+    var_one = n * p * (1 - p) * (A + n) / (A + 1)
+    assert np.all(np.abs(x / n_el - n * p) < 5 * np.sqrt(var_one / n_el))
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2small", "C5a", "C5b", "replace"])
+def test_posterior_win_probabilities_match_the_oracle(pkg, L, port, cfg):
+    """Posterior win probabilities, GPU vs oracle, within 4.5 sigma of the binomial Monte-Carlo error of the
+    difference. C1 is BASELINE config 1 in full."""
+    W = pkg.workloads
+    if cfg == "C1":
+        c = W.CONFIGS["C1"]
+        nc, mn, mx, a0, vd = c["n_candidates"], c["min_depth"], c["max_depth"], c["a0"], c["vd"]
+        prefs, offsets = W.observed_ballots("C1")
+        n_el, n_b, replace = c["n_elections"] * 4, c["n_ballots"], False
+    elif cfg == "C2small":
+        nc, mn, mx, a0, vd = 6, 0, 5, 1.0, False
+        prefs, offsets = W.wakehurst_sample(300, 2)
+        n_el, n_b, replace = 3000, 5000, False
+    elif cfg in ("C5a", "C5b"):
+        nc, mn, mx, vd = 8, 7, 7, True
+        a0 = 1e-3 if cfg == "C5a" else 1.0
+        prefs, offsets = W.plackett_luce_ballots(8, 0.1, 60, 5, None)
+        n_el, n_b, replace = 1500, 2000, False
+    else:
+        nc, mn, mx, a0, vd = 5, 0, 5, 1.0, False
+        prefs, offsets = W.plackett_luce_ballots(5, 0.2, 40, 6, [1, 1, 1, 1, 1, 2])
+        n_el, n_b, replace = 4000, 60, True
+    t, o = make_pair(pkg, port, nc, mn, mx, a0, vd, prefs, offsets)
+    wins = t.sample_posterior_counts(n_el, n_b, replace=replace, seed="WIN" + cfg)
+    gpu = wins / float(n_el)
+    freq, _ = o.sample_posterior(n_el, n_b, 1, replace, 4, "WIN" + cfg)
+    assert abs(gpu.sum() - 1) < 1e-12 and abs(freq.sum() - 1) < 1e-9
+    pooled = (gpu + freq) / 2
+    tol = 4.5 * np.sqrt(np.maximum(pooled * (1 - pooled), 1.0 / n_el) * 2 / n_el)
+    assert np.all(np.abs(gpu - freq) <= tol), (gpu.tolist(), freq.tolist())
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own behavioural tests, through the host API
+# ------------------------------------------------------------------------------------------------
+def test_posterior_shifts_after_observing_data(pkg, L):
+    """tests/testthat/test-posterior.R:1-22 and test-update_and_reset.R:1-30"""
+    pkg.set_seed(42)
+    dtree = pkg.dirtree(list("ABCD"))
+    prior = pkg.sample_posterior(dtree, 1000, 10)
+    for _ in range(5):
+        pkg.update(dtree, [list("ABCD")])
+    post_dt = pkg.sample_posterior(dtree, 1000, 10)
+    dtree.vd = True
+    post_d = pkg.sample_posterior(dtree, 1000, 10)
+    assert post_d["A"] > prior["A"] and post_dt["A"] > prior["A"]
+    assert all(post_d[c] < prior[c] and post_dt[c] < prior[c] for c in "BCD")
+    pkg.reset(dtree)
+    dtree.vd = False
+    again = pkg.sample_posterior(dtree, 1000, 10)
+    assert abs(again["A"] - prior["A"]) < 0.1 and dtree.n_observed == 0
+
+
+def test_posterior_is_uniform_when_a0_is_zero(pkg, L):
+    """tests/testthat/test-posterior.R:24-29"""
+    dtree = pkg.dirtree(list("ABCDEFGHIJ"), a0=0)
+    probs = np.array(list(pkg.sample_posterior(dtree, 1000, 10, seed="a0").values()))
+    assert abs(probs.sum() - 1) < 1e-12 and probs.var(ddof=1) < 1e-2
+
+
+def test_replace_gives_more_than_one_possible_winner(pkg, L):
+    """tests/testthat/test-posterior.R:71-93"""
+    dtree = pkg.dirtree(list("ABC"))
+    pkg.update(dtree, [list("ABC")] * 3)
+    without = pkg.sample_posterior(dtree, 100, 3, replace=False, seed="r")
+    assert without == {"A": 1.0, "B": 0.0, "C": 0.0}
+    with_r = pkg.sample_posterior(dtree, 1000, 3, replace=True, seed="r")
+    assert sum(v > 0 for v in with_r.values()) > 1
+
+
+def test_n_winners_and_error_paths(pkg, L):
+    dtree = pkg.dirtree(list("ABCDE"))
+    pkg.update(dtree, [list("ABCDE")] * 4 + [list("BACDE")] * 3)
+    two = pkg.sample_posterior(dtree, 500, 50, n_winners=2, seed="w")
+    assert abs(sum(two.values()) - 2.0) < 1e-12 and two["A"] > 0.8 and two["B"] > 0.8
+    with pytest.raises(pkg._native.DtreeError):
+        dtree.sample_posterior_counts(10, 50, n_winners=5)
+    with pytest.raises(ValueError):
+        pkg.sample_posterior(dtree, 10, 3)
+    # like the reference (R_tree.cpp:183-186) the native layer refuses n_ballots < n_observed even with replace
+    with pytest.raises(pkg._native.DtreeError) as ei:
+        pkg.sample_posterior(dtree, 10, 3, replace=True)
+    assert ei.value.code == pkg._native.ERR_STATE
+
+
+def test_abort_callback_stops_a_run(pkg, L):
+    """RcppThread::checkUserInterrupt (R_tree.cpp:222) -> dtree_set_abort_callback."""
+    dtree = pkg.dirtree(list("ABCDEFGH"))
+    calls = []
+
+    def cb(_):
+        calls.append(1)
+        return 1 if len(calls) >= 2 else 0
+
+    fn = pkg._native.ABORT_CB(cb)
+    lib = pkg._native.lib()
+    lib.dtree_set_abort_callback(dtree._h, fn, None)
+    dtree.tune(block_threads=32, blocks_per_sm=1)
+    with pytest.raises(pkg._native.DtreeError) as ei:
+        dtree.sample_posterior_counts(2_000_000, 50, seed="abort")
+    assert ei.value.code == pkg._native.ERR_ABORTED and len(calls) == 2
+    lib.dtree_set_abort_callback(dtree._h, C.cast(None, pkg._native.ABORT_CB), None)
+    assert int(dtree.sample_posterior_counts(100, 50, seed="abort").sum()) == 100
