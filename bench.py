@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — simulated IRV elections / second on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3] [--impl ours|reference]
+
+A *step* is one pass of the hot path (Dirichlet-tree posterior draw -> IRV -> win counts) over one
+batch of simulated elections of the named configuration, `--elections-per-gpu` per GPU (weak
+scaling: at 8 GPUs the default C3 step is exactly BASELINE's "100k elections sharded over 8 GPUs").
+Ranks simulate disjoint global election ranges, then all-reduce the <=32 win counts (NCCL).
+
+ value      tree already resident in HBM, win counts left on the device; CUDA events on the launch
+            stream, max over ranks.
+ e2e        the same batch through the host-buffer C-ABI call (dtree_sample_posterior) with the
+            device mirror invalidated first: CSR flatten + H2D of the tree, kernel, D2H of the counts.
+ roofline   simulate_kernel against measured HBM bandwidth, with SURVEY §8(d)'s algorithmic bytes
+            per election taken from the CPU oracle's counters on the same inputs.
+ cpu_baseline / --impl reference
+            the reference's own C++ (oracle/_ref, else the port) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_pkg  # noqa: E402
+
+METRIC = "simulated IRV elections/sec"
+SEED = "BENCHSEEDx"
+DEFAULT_EPG = {"C1": 1_000_000, "C2": 400_000, "C3": 12_500, "C4": 2_000, "C5": 100_000}
+
+
+def describe(name, cfg, epg):
+    return ("%s: %d candidates, %d observed ballots (%s), n_ballots=%d, min_depth=%d, max_depth=%d, a0=%g, vd=%s; "
+            "%d elections per GPU per step" % (name, cfg["n_candidates"], cfg["observed"][2 if cfg["observed"][0] == "pl" else 1],
+                                               "Plackett-Luce gamma=%g seed %d" % (cfg["observed"][1], cfg["observed"][3])
+                                               if cfg["observed"][0] == "pl" else "Wakehurst sample seed %d" % cfg["observed"][2],
+                                               cfg["n_ballots"], cfg["min_depth"], cfg["max_depth"], cfg["a0"], cfg["vd"], epg))
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def load_oracle():
+    from oracle import oracle
+    kind = "reference" if oracle.available("reference") else "port"
+    return oracle, oracle.load(kind), kind
+
+
+def cpu_run(olib, cfg, prefs, offsets, n_elections, threads, seed):
+    t = olib.tree(cfg["n_candidates"], cfg["min_depth"], cfg["max_depth"], cfg["a0"], cfg["vd"])
+    t.update((prefs, offsets))
+    freq, secs = t.sample_posterior(n_elections, cfg["n_ballots"], 1, False, threads, seed)
+    t.close()
+    return freq, secs
+
+
+def cpu_sample_size(cfg, threads):
+    """Elections for a bounded CPU sample: ~10-30 s of work on `threads` cores (per-election cost from BASELINE.md)."""
+    per_election = {4: 3e-5, 6: 1.2e-3, 8: 0.06, 10: 0.9, 20: 10.0}.get(cfg["n_candidates"], 0.5)
+    n = int(15.0 * threads / per_election)
+    return max(2 * threads, min(n, cfg["n_elections"]))
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + self.QUERY,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_reference(args, cfg, name):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    pkg_wl = load_pkg().workloads
+    oracle, olib, kind = load_oracle()
+    threads = host_threads()
+    prefs, offsets = pkg_wl.observed_ballots(name)
+    per_step = max(2 * threads, cpu_sample_size(cfg, threads) // 4)
+    t = olib.tree(cfg["n_candidates"], cfg["min_depth"], cfg["max_depth"], cfg["a0"], cfg["vd"])
+    t.update((prefs, offsets))
+    secs = []
+    for i in range(args.warmup + args.steps):
+        _, s = t.sample_posterior(per_step, cfg["n_ballots"], 1, False, threads, SEED + str(i))
+        if i >= args.warmup:
+            secs.append(s)
+    total = float(sum(secs))
+    value = per_step * args.steps / total
+    sample = "%d elections per step (of %d), %d threads, thread pool of R_tree.cpp:213-242" % (per_step, cfg["n_elections"], threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "elections/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": describe(name, cfg, per_step), "note": "CPU only; n_gpus is the launch shape, rank 0 does all the work"},
+        "cpu_baseline": {"value": value, "unit": "elections/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "elections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--elections-per-gpu", type=int, default=0)
+    ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--urn-max", type=int, default=-1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    pkg = load_pkg()
+    W = pkg.workloads
+    name = args.config
+    cfg = W.CONFIGS[name]
+    if args.impl == "reference":
+        return run_reference(args, cfg, name)
+
+    import torch
+    import torch.distributed as dist
+    from elections_dtree_b200 import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus %d must be launched with torch.distributed.run --nproc-per-node %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    epg = args.elections_per_gpu or DEFAULT_EPG[name]
+    nc = cfg["n_candidates"]
+    prefs, offsets = W.observed_ballots(name)
+    t = pkg.dirichlet_tree(W.candidate_names(nc), cfg["min_depth"], cfg["max_depth"], cfg["a0"], cfg["vd"], device=local)
+    t.update_indices(prefs, offsets)
+    if args.block_threads or args.blocks_per_sm:
+        t.tune(block_threads=args.block_threads, blocks_per_sm=args.blocks_per_sm)
+    if args.urn_max >= 0:
+        t.tune(urn_max=args.urn_max)
+    L = N.lib()
+    N.check(L.dtree_sync_device(t._h))
+    seed = SEED.encode()
+    stream = torch.cuda.current_stream(dev)
+    wins = torch.zeros(nc, dtype=torch.int64, device=dev)
+
+    total = torch.zeros(nc, dtype=torch.int64, device=dev)
+
+    def step(i):
+        # global election ids: step i covers [i*epg*world, (i+1)*epg*world); this rank's contiguous share
+        first = (i * world + rank) * epg
+        wins.zero_()
+        N.check(L.dtree_sample_posterior_device(t._h, first, epg, cfg["n_ballots"], 1, 0, seed, len(seed),
+                                                wins.data_ptr(), stream.cuda_stream))
+        if world > 1:
+            dist.all_reduce(wins, op=dist.ReduceOp.SUM)
+        total.add_(wins)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    N.check(L.dtree_sample_posterior_finish(t._h, stream.cuda_stream))
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kernel_ev = []
+    total.zero_()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        first = ((args.warmup + i) * world + rank) * epg
+        wins.zero_()
+        k0.record(stream)
+        N.check(L.dtree_sample_posterior_device(t._h, first, epg, cfg["n_ballots"], 1, 0, seed, len(seed),
+                                                wins.data_ptr(), stream.cuda_stream))
+        k1.record(stream)
+        kernel_ev.append((k0, k1))
+        if world > 1:
+            dist.all_reduce(wins, op=dist.ReduceOp.SUM)
+        total.add_(wins)
+        ev[i + 1].record(stream)
+    barrier()
+    N.check(L.dtree_sample_posterior_finish(t._h, stream.cuda_stream))
+    stats = t.last_stats()
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_ev]))
+    el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(el.item())
+    total_wins = int(total.sum().item())
+    assert total_wins == epg * world * args.steps, (total_wins, epg * world * args.steps)
+    value = epg * world * args.steps / (elapsed_ms / 1e3)
+
+    # ---- e2e: host buffers through the C ABI, mirror invalidated so that the tree upload is inside -------------
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d0 = t.last_stats()["h2d_bytes"]
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        N.check(L.dtree_invalidate_device(t._h))
+        first = ((args.warmup + args.steps + i) * world + rank) * epg
+        w = t.sample_posterior_counts(epg, cfg["n_ballots"], seed=SEED, first_election=first)
+        if world > 1:
+            wt = torch.from_numpy(w.astype(np.int64)).to(dev)
+            dist.all_reduce(wt, op=dist.ReduceOp.SUM)
+            w = wt.cpu().numpy()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2.item())
+    h2d = (t.last_stats()["h2d_bytes"] - h2d0) // e2e_steps
+    e2e = {"value": epg * world * e2e_steps / e2e_s, "unit": "elections/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(nc * 8), "steps": e2e_steps}
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline denominators from the CPU oracle's counters on the same inputs -----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # the kernel's own per-election counters (exact for what was launched)
+    S_k = stats["slots"] / max(stats["elections"], 1)
+    E_k = stats["entries"] / max(stats["elections"], 1) + (len(t.observed_indices()[2]))
+    R_k = stats["irv_rereads"] / max(stats["elections"], 1)
+    cpu_baseline = None
+    b_alg = 4 * S_k + 32 * E_k + 16 * R_k + 8 * nc
+    denominators = {"source": "kernel counters", "S": S_k, "E": E_k, "R": R_k}
+    if not args.no_cpu_baseline:
+        oracle, olib, kind = load_oracle()
+        port = oracle.load("port")
+        ot = port.tree(nc, cfg["min_depth"], cfg["max_depth"], cfg["a0"], cfg["vd"])
+        ot.update((prefs, offsets))
+        n_stat = 3 if nc >= 10 else 20
+        st = [ot.election_stats(cfg["n_ballots"], False, 1000 + i) for i in range(n_stat)]
+        ot.close()
+        S, E, R = (float(np.mean([s[k] for s in st])) for k in ("S", "E", "R"))
+        b_alg = 4 * S + 32 * E + 16 * R + 8 * nc
+        denominators = {"source": "oracle counters, mean of %d elections" % n_stat, "S": S, "E": E, "R": R,
+                        "V_gamma": float(np.mean([s["V_gamma"] for s in st])),
+                        "kernel_counters": {"S": S_k, "E": E_k, "R": R_k,
+                                            "gammas": stats["gammas"] / max(stats["elections"], 1),
+                                            "binomial_attempts": stats["binomial_attempts"] / max(stats["elections"], 1),
+                                            "items": stats["items"] / max(stats["elections"], 1),
+                                            "urn_items": stats["urn_items"] / max(stats["elections"], 1)}}
+        threads = host_threads()
+        n_cpu = cpu_sample_size(cfg, threads)
+        _, secs = cpu_run(olib, cfg, prefs, offsets, n_cpu, threads, SEED)
+        cpu_baseline = {"value": n_cpu / secs, "unit": "elections/s", "cores": threads, "kind": kind,
+                        "sample": "%d elections of the same workload in %.1f s, %d threads (R_tree.cpp:213-242 pool)" % (n_cpu, secs, threads)}
+    achieved = b_alg * epg / (kernel_ms / 1e3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "elections/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 Gamma variates + f64 binomial rejection; u32 counts/tallies", "data": "synthetic",
+        "config": {"workload": describe(name, cfg, epg), "global_elections_per_step": epg * world,
+                   "cache": "working set larger than L2: %.1f GB of per-election scratch streamed per step" % (stats["scratch_bytes"] / 1e9),
+                   "parallelism": "elections sharded over %d GPU(s), tree replicated, one all-reduce of %d win counts" % (world, nc),
+                   "seed": SEED},
+        "e2e": e2e, "gpu_launches": int(stats["launches"]) * args.steps,
+        "roofline": {"kernel": "simulate_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_election": b_alg, "kernel_ms_per_launch": kernel_ms,
+                     "denominators": denominators},
+        "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -7,6 +7,6 @@ hot path (sample_posterior / sample_predictive on a Dirichlet-tree + IRV social 
     workloads.py the pinned synthetic inputs of the benchmark configurations
 """
 from . import workloads  # noqa: F401
-from . import _native  # noqa: F401
+from . import _native, sharding  # noqa: F401
 from .api import (dirichlet_tree, dirtree, gseed, irv_indices, reset, sample_posterior,  # noqa: F401
                   sample_predictive, set_seed, social_choice, update)
