@@ -128,6 +128,7 @@ struct dtree {
   // tuning
   int block_threads = 0, blocks_per_sm = 0;
   uint32_t urn_max = 8;
+  int mode = 1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel)
   // callbacks, stats
   int (*should_abort)(void *) = nullptr;
   void *abort_user = nullptr;
@@ -195,7 +196,9 @@ struct Plan {
   int W, block, grid, blocks_per_sm;
   bool log_gamma;
   uint32_t cap_items, cap_entries;
-  uint64_t stride;
+  uint64_t stride;        // scratch bytes per block (materialising kernel) or per warp (deferred kernel)
+  uint64_t stride_block;  // scratch bytes per block
+  bool deferred = false;
 };
 
 template <int W>
@@ -222,6 +225,7 @@ int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, P
             : pl.W == 2 ? scratch_bytes<2>(pl.cap_items, pl.cap_entries, nobs)
                         : scratch_bytes<3>(pl.cap_items, pl.cap_entries, nobs);
   pl.stride = (pl.stride + 255) & ~255ull;
+  pl.stride_block = pl.stride;
 
   int block = t->block_threads;
   if (block == 0) {
@@ -232,8 +236,6 @@ int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, P
   bool okb = false;
   for (int i = 0; i < kNumBlockSizes; ++i) okb |= (kBlockSizes[i] == block);
   if (!okb) return fail(DTREE_ERR_ARG, "block_threads must be one of 32, 64, 128, 256");
-  if (simulate_smem_bytes(nc, block) + 8192 > t->smem_optin)
-    return fail(DTREE_ERR_CUDA, "not enough shared memory per block");
   pl.block = block;
   int occ = pl.W == 1 ? simulate_blocks_per_sm<1>(nc, block, pl.log_gamma)
           : pl.W == 2 ? simulate_blocks_per_sm<2>(nc, block, pl.log_gamma)
@@ -252,6 +254,34 @@ int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, P
   if (pl.stride > budget) return fail(DTREE_ERR_CUDA, "one election needs %llu bytes of scratch, more than the device has free",
                                       (unsigned long long)pl.stride);
   pl.grid = (int)grid;
+  return DTREE_OK;
+}
+
+// Launch shape and scratch of deferred_kernel: one warp per election, three item arrays per warp
+// (parked nodes + two frontiers), each able to hold every distinct prefix an election can touch.
+int make_plan_deferred(dtree *t, uint32_t n_sample, uint32_t n_elections, Plan &pl) {
+  const HostParams &P = t->tree.P;
+  pl.W = 1;
+  pl.log_gamma = device_params(P).small_alpha != 0;
+  pl.block = 128;
+  if (t->block_threads == 64 || t->block_threads == 128 || t->block_threads == 256) pl.block = t->block_threads;
+  int occ = deferred_blocks_per_sm(pl.block, pl.log_gamma);
+  if (occ <= 0) return fail(DTREE_ERR_CUDA, "deferred kernel cannot be resident (%s)", cudaGetErrorString(cudaGetLastError()));
+  if (t->blocks_per_sm > 0) occ = std::min(occ, t->blocks_per_sm);
+  pl.blocks_per_sm = occ;
+  const int wpb = pl.block / 32;
+  uint64_t worst = (uint64_t)n_sample + t->tree.n_nodes() + 1;
+  pl.cap_items = (uint32_t)std::min<uint64_t>(worst, 0xFFFFFFF0ull);
+  pl.cap_entries = 0;
+  pl.stride = ((uint64_t)3 * pl.cap_items * sizeof(Item<1>) + 255) & ~255ull;  // per warp
+  uint64_t grid = std::min<uint64_t>((uint64_t)occ * t->sm_count, ((uint64_t)n_elections + wpb - 1) / wpb);
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  uint64_t budget = (uint64_t)((double)(free_b + t->d_scratch.n) * 0.6);
+  uint64_t fit = budget / (pl.stride * wpb);
+  if (fit == 0) return fail(DTREE_ERR_CUDA, "not enough device memory for one block of deferred scratch");
+  pl.grid = (int)std::max<uint64_t>(1, std::min(grid, fit));
+  pl.stride_block = pl.stride * wpb;
   return DTREE_OK;
 }
 
@@ -275,6 +305,7 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
 
 cudaError_t launch(const Plan &pl, const SimArgs &a, cudaStream_t s) {
   LaunchCfg cfg{pl.block, pl.log_gamma, pl.grid, s};
+  if (pl.deferred) return launch_deferred(a, cfg);
   return pl.W == 1 ? launch_simulate<1>(a, cfg) : pl.W == 2 ? launch_simulate<2>(a, cfg) : launch_simulate<3>(a, cfg);
 }
 
@@ -303,9 +334,10 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   const bool use_obs = !replace;
   const uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->tree.n_observed();
   Plan pl;
-  rc = make_plan(t, n_sample, n_elections, use_obs, pl);
+  pl.deferred = t->mode == 1;
+  rc = pl.deferred ? make_plan_deferred(t, n_sample, n_elections, pl) : make_plan(t, n_sample, n_elections, use_obs, pl);
   if (rc) return rc;
-  CUDA_TRY(t->d_scratch.reserve(pl.stride * pl.grid));
+  CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));
   CUDA_TRY(t->d_counter.reserve(1));
   CUDA_TRY(t->d_error.reserve(1));
   CUDA_TRY(t->d_stats.reserve(kStatCount));
@@ -320,6 +352,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   a.obs_first = t->d_obs_first.p;
   a.obs_tally0 = t->d_obs_tally0.p;
   a.n_obs = use_obs ? t->n_obs_entries : 0;
+  a.use_obs = use_obs ? 1 : 0;
   a.seed = hash_seed(seed, seed_len);
   a.n_sample = n_sample;
   a.n_winners = n_winners;
@@ -328,7 +361,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
 
   // One launch per wave. Without an abort callback the whole range is one wave.
   uint32_t wave = n_elections;
-  if (t->should_abort) wave = (uint32_t)std::min<uint64_t>(n_elections, (uint64_t)pl.grid * 64);
+  if (t->should_abort) wave = (uint32_t)std::min<uint64_t>(n_elections, (uint64_t)pl.grid * (pl.deferred ? 4096 : 64));
   uint64_t launches = 0;
   for (uint32_t done = 0; done < n_elections; done += wave) {
     uint32_t n = std::min(wave, n_elections - done);
@@ -345,7 +378,8 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   }
   t->stats[0] = launches;
   t->stats[1] = n_elections;
-  t->stats[7] = pl.stride * pl.grid;
+  t->stats[7] = pl.stride_block * pl.grid;
+  t->stats[12] = pl.deferred ? 1 : 0;
   if (!sync_at_end) return DTREE_OK;
   CUDA_TRY(cudaStreamSynchronize(s));
   int err = 0;
@@ -805,7 +839,10 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   if (!t || !key) return fail(DTREE_ERR_ARG, "null argument");
   if (!strcmp(key, "block_threads")) t->block_threads = (int)value;
   else if (!strcmp(key, "blocks_per_sm")) t->blocks_per_sm = (int)value;
-  else if (!strcmp(key, "urn_max")) {
+  else if (!strcmp(key, "mode")) {
+    if (value != 0 && value != 1) return fail(DTREE_ERR_ARG, "mode must be 0 (materialise) or 1 (deferred)");
+    t->mode = (int)value;
+  } else if (!strcmp(key, "urn_max")) {
     if (value < 0 || value > 8) return fail(DTREE_ERR_ARG, "urn_max must be in [0, 8]");
     t->urn_max = (uint32_t)value;
   } else return fail(DTREE_ERR_ARG, "unknown tuning key '%s'", key);

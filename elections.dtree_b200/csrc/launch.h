@@ -16,7 +16,8 @@ struct LaunchCfg {
 constexpr int kBlockSizes[] = {32, 64, 128, 256};
 constexpr int kNumBlockSizes = 4;
 
-inline size_t simulate_smem_bytes(uint32_t nc, int block) { return (size_t)block * ((nc + 1u) | 1u) * sizeof(float); }
+// All shared memory of simulate_kernel is static (per-warp tiles); nothing dynamic to request.
+inline size_t simulate_smem_bytes(uint32_t, int) { return 0; }
 
 // Launches simulate_kernel<W, block, log>. Returns cudaErrorInvalidValue for an unsupported block size.
 template <int W>
@@ -24,6 +25,10 @@ cudaError_t launch_simulate(const SimArgs &a, const LaunchCfg &cfg);
 // Resident blocks per SM for that instantiation (occupancy API).
 template <int W>
 int simulate_blocks_per_sm(uint32_t nc, int block, bool log_gamma);
+
+// deferred_kernel (deferred.cuh): one warp per election, `block` threads per block (64, 128 or 256).
+cudaError_t launch_deferred(const SimArgs &a, const LaunchCfg &cfg);
+int deferred_blocks_per_sm(int block, bool log_gamma);
 
 // Stand-alone IRV over entries already placed in block 0's scratch (dtree_irv).
 struct IrvArgs {

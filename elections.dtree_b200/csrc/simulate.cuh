@@ -1,69 +1,29 @@
-// simulate.cuh — the posterior-simulation kernel: one thread block simulates one election at a
-// time (persistent blocks pulling election ids from a counter):
+// simulate.cuh — the posterior-simulation kernel. One thread block simulates one election at a
+// time (persistent blocks pull election ids from a counter):
 //
 //   (a)+(b) level-synchronous expansion of the Dirichlet-tree (IRVNode::sample, irv_node.cpp:107-174,
-//           and lazyIRVBallots, :27-84): the frontier of one depth is processed in chunks of BLOCK
-//           items; Gamma variates are drawn one thread per (item, outcome) into shared memory, then
-//           one thread per item normalises them and splits the item's count with sequential
-//           binomials (rMultinomial, distributions.cpp:21-53); children and finished ballots are
-//           compacted with a block-wide prefix sum into the next frontier / the entry list;
+//           and lazyIRVBallots, :27-84). The frontier of one depth lives in a two-ended queue in
+//           global memory: items whose count is small enough for the Polya-urn shortcut grow from
+//           the front, the others from the back. Each WARP repeatedly claims a chunk of items and
+//           processes it on its own (no block barrier inside a level):
+//             - Gamma variates, one lane per (item, outcome), into a per-warp shared-memory tile;
+//             - a binary tree of partial sums over each item's outcomes (bottom-up), then the
+//               item's count is pushed down that tree with one binomial per internal node
+//               (top-down), again one lane per (item, tree node). This is rMultinomial
+//               (distributions.cpp:21-53) with the conditional binomials arranged as a balanced
+//               tree instead of a chain: the same multinomial law, log2(d) dependent steps instead
+//               of d-1, and no 1-x cancellation because both child sums are at hand;
+//             - children / finished ballots are compacted with warp ballots and appended to the
+//               next frontier / the entry list with one shared-memory atomic per warp and queue;
 //   (c)     IRV elimination over the election's (ballot, count) entries plus the shared observed
 //           entries (socialChoiceIRV, irv_ballot.cpp:42-138);
 //   (d)     win counts accumulated per block and flushed with one atomic per candidate.
 #pragma once
 #include <cstdint>
 
-#include "dtree_types.h"
-#include "rng.cuh"
-#include "variates.cuh"
+#include "split.cuh"
 
 namespace dtb {
-
-template <int W>
-struct alignas(16) Item {
-  BallotKey<W> prefix;  // candidates chosen so far
-  uint64_t node_key;    // RNG identity of the node (hash chain over the prefix)
-  uint32_t count;       // ballots to distribute below this node
-  int32_t node;         // CSR node id, -1 = uninitialised (prior-only) subtree
-  uint32_t used;        // bit c set <=> candidate c is in the prefix
-  uint32_t pad_;
-};
-
-enum StatSlot {
-  kStatEntries = 0, kStatItems, kStatGammas, kStatBinomials, kStatRereads, kStatSlots, kStatUrnItems, kStatCount
-};
-
-struct SimArgs {
-  DeviceParams P;
-  DeviceTree T;
-  // observed ballots (replace == false): shared by all elections
-  const void *obs_key;        // BallotKey<W>[n_obs]
-  const uint32_t *obs_cnt;
-  const uint8_t *obs_first;   // first preference, 0xFF for a blank ballot
-  const uint32_t *obs_tally0; // [nc] first-preference tallies of the observed ballots
-  uint32_t n_obs;
-  // job
-  uint64_t seed;
-  uint64_t first_election;
-  uint32_t n_elections;
-  uint32_t n_sample;          // ballots to draw per election (N, or N - n_observed)
-  uint32_t n_winners;
-  uint32_t urn_max;
-  int run_irv;                // 0: expansion only (predictive / posterior_set dumps)
-  // per-block scratch
-  uint8_t *scratch;
-  uint64_t scratch_stride;    // bytes per block
-  uint32_t cap_items;         // frontier capacity (items) per buffer
-  uint32_t cap_entries;
-  // outputs
-  unsigned long long *win_counts;  // [nc], added to
-  uint8_t *elim_orders;            // NULL or [n_elections * nc]
-  uint32_t *entry_count_out;       // dump mode: number of entries of the (single) election
-  uint32_t *tie_rounds_out;        // NULL or [n_elections]
-  unsigned int *work_counter;      // next election index to hand out
-  int *error_flag;                 // set to 1 on scratch overflow
-  unsigned long long *stats;       // [kStatCount]
-};
 
 // Where the pieces of one block's scratch live.
 template <int W>
@@ -90,85 +50,15 @@ struct Scratch {
   }
 };
 
-// ---- block-wide helpers ------------------------------------------------------------------------
-
-// Exclusive prefix sum of one uint32 per thread; returns this thread's offset, *total = block sum.
-template <int BLOCK>
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_warp /*[33]*/, uint32_t *total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = (BLOCK + 31) / 32;
-  uint32_t x = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (NW == 1) {
-    *total = __shfl_sync(0xffffffffu, x, 31);
-    return x - v;
-  }
-  if (lane == 31) s_warp[warp] = x;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = lane < NW ? s_warp[lane] : 0u;
-    uint32_t xs = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
-      if (lane >= o) xs += y;
-    }
-    if (lane < NW) s_warp[lane] = xs - w;
-    if (lane == NW - 1) s_warp[32] = xs;
-  }
-  __syncthreads();
-  uint32_t off = s_warp[warp] + x - v;
-  *total = s_warp[32];
-  __syncthreads();  // s_warp may be reused immediately by the caller
-  return off;
-}
-
-// Adds `amount` to s_tally[cand] for every lane with valid; lanes naming the same candidate are
-// combined first so that a warp issues one shared-memory atomic per distinct candidate.
-__device__ __forceinline__ void warp_tally_add(uint32_t *s_tally, bool valid, uint32_t cand, uint32_t amount) {
-  uint32_t pending = __ballot_sync(0xffffffffu, valid);
-  while (pending) {
-    int leader = __ffs(pending) - 1;
-    uint32_t c0 = __shfl_sync(0xffffffffu, cand, leader);
-    uint32_t same = __ballot_sync(0xffffffffu, valid && cand == c0);
-    uint32_t sum = __reduce_add_sync(0xffffffffu, (valid && cand == c0) ? amount : 0u);
-    if ((int)(threadIdx.x & 31) == leader) atomicAdd(&s_tally[c0], sum);
-    pending &= ~same;
-  }
-}
-
-// i-th (0-based) candidate not in `used`, ascending.
-__device__ __forceinline__ uint32_t nth_unused(uint32_t used, uint32_t nc, uint32_t i) {
-  uint32_t avail = ~used & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
-  for (uint32_t k = 0; k < i; ++k) avail &= avail - 1u;
-  return (uint32_t)__ffs(avail) - 1u;
-}
-
-// First standing preference of a ballot: scans from the front, skipping eliminated candidates.
-template <int W>
-__device__ __forceinline__ uint32_t first_standing(const BallotKey<W> &k, uint32_t len, uint32_t eliminated) {
-  for (uint32_t j = 0; j < len; ++j) {
-    uint32_t c = key_get<W>(k, (int)j);
-    if (!(eliminated >> c & 1u)) return c;
-  }
-  return 0xFFu;
-}
-
-// ---- shared-memory layout ------------------------------------------------------------------------
-// Dynamic shared memory: BLOCK * dstride floats (the Gamma / count matrix, column = item).
 template <int BLOCK>
 struct SharedFixed {
-  uint64_t node_key[BLOCK];
-  uint32_t nbase[BLOCK];       // first CSR slot of the item's node, UINT32_MAX for a prior-only item
-  uint32_t count[BLOCK];
-  uint16_t gamma_list[BLOCK];  // chunk-local indices of the items that need Gamma variates
-  uint32_t n_gamma;
-  uint32_t warp_scan[33];
-  uint32_t n_in, n_out, n_entries;
+  // frontier bookkeeping of the level being processed / produced
+  uint32_t n_small, n_big;        // items at the front (small counts) / back (Gamma path) of the input queue
+  uint32_t next_small, next_big;  // chunk cursors
+  uint32_t out_small, out_big;    // items appended to the output queue
+  uint32_t n_entries;
+  uint32_t overflow;
+  // IRV
   uint32_t tally[kMaxCandidates];
   uint32_t wins[kMaxCandidates];
   uint32_t eliminated, chosen, tie_rounds;
@@ -176,17 +66,158 @@ struct SharedFixed {
   uint8_t order[kMaxCandidates];
 };
 
+// One thread finishes the whole subtree below a small item (count <= urn_max <= 8): a depth-first
+// walk with an explicit stack of at most 8 frames (every frame holds >= 1 of the <= 8 ballots),
+// applying the urn at each node and emitting finished ballots straight into the entry list.
+// The draws at a node depend only on (election, node), so this gives the same ballots as pushing
+// the item through the level-synchronous queue would.
+template <int W, int BLOCK>
+__device__ void walk_small_item(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, const Item<W> &root,
+                                uint32_t root_depth, const RngKey key, uint32_t *stat) {
+  Item<W> stack[8];
+  int top = 0;
+  stack[0] = root;
+  stack[0].pad_ = root_depth;
+  top = 1;
+  const uint32_t nc = a.P.nc;
+  while (top > 0) {
+    Item<W> f = stack[--top];
+    const LevelInfo lv = level_info(a.P, f.pad_);
+    const uint32_t nbase = f.node >= 0 ? a.T.node_base[f.node] : 0xFFFFFFFFu;
+    stat[kStatItems] += 1;
+    stat[kStatUrnItems] += 1;
+    if (f.node >= 0) stat[kStatSlots] += lv.d;
+    const uint64_t picks = urn_picks(a, lv, nbase, f.count, key, f.node_key);
+    // group equal outcomes
+    uint32_t done = 0;  // bit b set: ball b already accounted for
+    for (uint32_t b = 0; b < f.count; ++b) {
+      if (done >> b & 1u) continue;
+      const uint32_t slot = (uint32_t)(picks >> (8u * b)) & 0xFFu;
+      uint32_t c = 1;
+      for (uint32_t b2 = b + 1; b2 < f.count; ++b2)
+        if (((uint32_t)(picks >> (8u * b2)) & 0xFFu) == slot) {
+          ++c;
+          done |= 1u << b2;
+        }
+      BallotKey<W> pk = f.prefix;
+      uint32_t cand = 0;
+      const bool stop = slot == lv.K;  // only possible when lv.T
+      if (!stop) {
+        cand = nbase != 0xFFFFFFFFu ? (uint32_t)a.T.slot_cand[nbase + slot] : nth_unused(f.used, nc, slot);
+        key_set<W>(pk, (int)lv.depth, cand);
+      }
+      if (stop || lv.leaf_children) {
+        const uint32_t eo = coalesced_reserve(&sm.n_entries);
+        if (eo < a.cap_entries) {
+          sc.ent_key[eo] = pk;
+          sc.ent_cnt[eo] = c;
+          sc.ent_len[eo] = (uint8_t)(stop ? lv.depth : lv.depth + 1);
+        } else {
+          sm.overflow = 1;
+        }
+      } else {
+        Item<W> ch;
+        ch.prefix = pk;
+        ch.node_key = child_node_key(f.node_key, cand);
+        ch.count = c;
+        ch.node = nbase != 0xFFFFFFFFu ? a.T.slot_child[nbase + slot] : -1;
+        ch.used = f.used | (1u << cand);
+        ch.pad_ = lv.depth + 1;
+        stack[top++] = ch;
+      }
+    }
+  }
+}
+
+// One warp expands one chunk of m items of the same depth whose counts exceed urn_max.
+template <int W, int BLOCK, bool LOG>
+__device__ void expand_chunk(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, WarpTile<W> &wt,
+                             const Item<W> *in, uint32_t m, const LevelInfo &lv, int log_dp, Item<W> *out,
+                             const RngKey key, uint32_t *stat) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nc = a.P.nc;
+  const uint32_t d = lv.d, K = lv.K;
+  const uint32_t dp = 1u << log_dp, stride = 2u * dp + 1u;
+
+  for (uint32_t it = lane; it < m; it += 32) {
+    Item<W> x = in[it];
+    x.pad_ = lv.depth;
+    wt.item[it] = x;
+    wt.nbase[it] = x.node >= 0 ? a.T.node_base[x.node] : 0xFFFFFFFFu;
+    stat[kStatItems] += 1;
+    if (x.node >= 0) stat[kStatSlots] += d;
+  }
+  __syncwarp();
+  split_items<W, LOG>(a, wt, m, log_dp, key, stat);
+
+  // ---- emission: one lane per (item, outcome); ballots for warp-level compaction -----------------
+  for (uint32_t base = 0; base < (m << log_dp); base += 32) {
+    const uint32_t p = base + lane;
+    const uint32_t it = p >> log_dp, slot = p & (dp - 1u);
+    uint32_t c = 0;
+    if (p < (m << log_dp) && slot < d) c = wt.val[it * stride + dp + slot];
+    // destination: 0 none, 1 entry, 2 small-count queue, 3 big queue
+    int dest = 0;
+    if (c) {
+      if (slot == K || lv.leaf_children) dest = 1;  // slot K: the ballot stops here (only when T)
+      else dest = c <= a.urn_max ? 2 : 3;
+    }
+    const uint32_t eo = warp_reserve(&sm.n_entries, dest == 1, lane);
+    const uint32_t so = warp_reserve(&sm.out_small, dest == 2, lane);
+    const uint32_t bo = warp_reserve(&sm.out_big, dest == 3, lane);
+    if (dest == 0) continue;
+    const Item<W> &par = wt.item[it];
+    BallotKey<W> pk = par.prefix;
+    uint32_t cand = 0;
+    const uint32_t nb = wt.nbase[it];
+    if (slot != K) {
+      cand = nb != 0xFFFFFFFFu ? (uint32_t)a.T.slot_cand[nb + slot] : nth_unused(par.used, nc, slot);
+      key_set<W>(pk, (int)lv.depth, cand);
+    }
+    if (dest == 1) {
+      if (eo < a.cap_entries) {
+        sc.ent_key[eo] = pk;
+        sc.ent_cnt[eo] = c;
+        sc.ent_len[eo] = (uint8_t)(slot == K ? lv.depth : lv.depth + 1);
+      } else {
+        sm.overflow = 1;
+      }
+    } else {
+      Item<W> ch;
+      ch.prefix = pk;
+      ch.node_key = child_node_key(par.node_key, cand);
+      ch.count = c;
+      ch.node = nb != 0xFFFFFFFFu ? a.T.slot_child[nb + slot] : -1;
+      ch.used = par.used | (1u << cand);
+      ch.pad_ = lv.depth + 1;
+      // two-ended queue: small items from the front, big items from the back; they must not meet.
+      // Both cursors already include this lane's reservation, so the test is conservative.
+      if (sm.out_small + sm.out_big > a.cap_items) {
+        sm.overflow = 1;
+      } else if (dest == 2) {
+        out[so] = ch;
+      } else {
+        out[a.cap_items - 1u - bo] = ch;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // One election's expansion. Leaves the entries in sc.ent_* and their number in sm.n_entries.
 template <int W, int BLOCK, bool LOG>
-__device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, float *s_val,
+__device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, WarpTile<W> *tiles,
                                 const RngKey key, uint32_t *stat) {
+  typedef Chunk<W> C;
   const uint32_t nc = a.P.nc;
-  const int tid = threadIdx.x;
-  const uint32_t dstride = (nc + 1u) | 1u;  // odd: column accesses are bank-conflict free
+  const int tid = threadIdx.x, lane = tid & 31;
+  WarpTile<W> &wt = tiles[tid >> 5];
 
   if (tid == 0) {
     sm.n_entries = 0;
-    sm.n_in = a.n_sample > 0 ? 1u : 0u;
+    sm.overflow = 0;
+    sm.n_small = 0;
+    sm.n_big = 0;
     if (a.n_sample > 0) {
       Item<W> root;
 #pragma unroll
@@ -196,231 +227,65 @@ __device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BL
       root.node = 0;
       root.used = 0;
       root.pad_ = 0;
-      sc.frontier[0][0] = root;
+      if (a.n_sample <= a.urn_max) {
+        sc.frontier[0][0] = root;
+        sm.n_small = 1;
+      } else {
+        sc.frontier[0][a.cap_items - 1] = root;
+        sm.n_big = 1;
+      }
     }
   }
   __syncthreads();
 
   int cur = 0;
   for (uint32_t depth = 0; depth + 1 < nc; ++depth) {
-    const uint32_t n_in = sm.n_in;
-    if (n_in == 0) break;
-    const uint32_t K = nc - depth;
-    const bool T = depth >= a.P.min_depth;
-    const uint32_t d = K + (T ? 1u : 0u);
-    const float a_prior = a.P.a_prior[depth];
-    // irv_node.cpp:136 (depth == maxDepth-1) and :46 (child depth == nc-1 or == maxDepth)
-    const bool leaf_children = (depth == a.P.leaf_depth) || (depth + 2 == nc);
+    const uint32_t n_small = sm.n_small, n_big = sm.n_big;
+    if (n_small + n_big == 0) break;
+    const LevelInfo lv = level_info(a.P, depth);
     const Item<W> *in = sc.frontier[cur];
     Item<W> *out = sc.frontier[cur ^ 1];
-    if (tid == 0) sm.n_out = 0;
-    __syncthreads();
-
-    for (uint32_t base = 0; base < n_in; base += BLOCK) {
-      const uint32_t gi = base + tid;
-      const bool active = gi < n_in;
-      Item<W> it;
-      bool use_gamma = false;
-      if (tid == 0) sm.n_gamma = 0;
-      __syncthreads();
-      if (active) {
-        it = in[gi];
-        sm.node_key[tid] = it.node_key;
-        sm.nbase[tid] = it.node >= 0 ? a.T.node_base[it.node] : 0xFFFFFFFFu;
-        sm.count[tid] = it.count;
-        use_gamma = it.count > a.urn_max;
-      }
-      {  // compact the Gamma-mode items of this chunk
-        uint32_t m = __ballot_sync(0xffffffffu, use_gamma);
-        uint32_t wbase = 0;
-        if ((tid & 31) == 0 && m) wbase = atomicAdd(&sm.n_gamma, (uint32_t)__popc(m));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (use_gamma) sm.gamma_list[wbase + __popc(m & ((1u << (tid & 31)) - 1u))] = (uint16_t)tid;
-      }
-      __syncthreads();
-
-      // ---- (a) Gamma variates: one thread per (item, outcome) --------------------------------
-      {
-        const uint32_t total = sm.n_gamma * d;
-        for (uint32_t s = tid; s < total; s += BLOCK) {
-          const uint32_t li = sm.gamma_list[s / d];
-          const uint32_t slot = s % d;  // slot K is the stop outcome (present only when T)
-          const uint32_t nb = sm.nbase[li];
-          float alpha = a_prior;
-          if (nb != 0xFFFFFFFFu) alpha = __fadd_rn((float)a.T.slot_count[nb + slot], a_prior);
-          float g;
-          if (alpha > 0.0f) {
-            uint32_t att = 0;
-            g = gamma_variate<LOG>(alpha, key, sm.node_key[li], slot, att);
-            stat[kStatGammas] += 1;
-          } else {
-            g = LOG ? -INFINITY : 0.0f;  // Gamma(0) is the point mass at 0
-          }
-          s_val[li * dstride + slot] = g;
-        }
-      }
-      __syncthreads();
-
-      // ---- (b) split the item's count over its outcomes: one thread per item -------------------
-      uint32_t n_child = 0, n_ent = 0;
-      float *col = s_val + tid * dstride;
-      if (active) {
-        stat[kStatItems] += 1;
-        if (it.node >= 0) stat[kStatSlots] += d;
-        const uint32_t nbase = sm.nbase[tid];
-        if (use_gamma) {
-          bool one_hot = false;
-          if (LOG) {
-            float mx = -INFINITY;
-            for (uint32_t i = 0; i < d; ++i) mx = fmaxf(mx, col[i]);
-            if (mx == -INFINITY) {
-              one_hot = true;  // every parameter is 0: distributions.cpp:69-77
-            } else {
-              for (uint32_t i = 0; i < d; ++i) col[i] = __expf(__fadd_rn(col[i], -mx));
-            }
-          } else {
-            float sum = 0.0f;
-            for (uint32_t i = 0; i < d; ++i) sum = __fadd_rn(sum, col[i]);
-            one_hot = !(sum > 0.0f);
-          }
-          if (one_hot) {
-            U4 r = node_random(key, it.node_key, kStreamOneHot, 0u);
-            uint32_t pick = uniform_below(r.x, d);
-            for (uint32_t i = 0; i < d; ++i) col[i] = __uint_as_float(i == pick ? it.count : 0u);
-          } else {
-            // Conditional probabilities from suffix sums: outcome i takes Binomial(remaining,
-            // g_i / sum_{j>=i} g_j). The smaller of (p, 1-p) is stored, negated when it is 1-p, so
-            // that neither tail loses precision.
-            float suffix = 0.0f;
-            for (int i = (int)d - 1; i >= 0; --i) {
-              float g = col[i];
-              float tot = __fadd_rn(suffix, g);
-              float v = 0.0f;
-              if (tot > 0.0f) v = (g <= suffix) ? __fdividef(g, tot) : -__fdividef(suffix, tot);
-              col[i] = v;
-              suffix = tot;
-            }
-            uint32_t remaining = it.count;
-            for (uint32_t i = 0; i < d; ++i) {
-              float v = col[i];
-              const bool flip = (__float_as_uint(v) >> 31) != 0u;
-              uint32_t att = 0;
-              uint32_t k = binomial_small_p(remaining, fabsf(v), key, it.node_key, i, att);
-              stat[kStatBinomials] += att;
-              if (flip) k = remaining - k;
-              remaining -= k;
-              col[i] = __uint_as_float(k);
-            }
-          }
-        } else {
-          // Polya urn for small counts: ball b copies a uniformly chosen earlier ball with
-          // probability b / (A + b), else draws a fresh outcome with probability alpha_i / A.
-          // Exactly Dirichlet-multinomial, no Gamma or binomial variates needed.
-          stat[kStatUrnItems] += 1;
-          for (uint32_t i = 0; i < d; ++i) col[i] = __uint_as_float(0u);
-          float A;
-          if (it.node >= 0) {
-            uint32_t tot = 0;
-            for (uint32_t i = 0; i < d; ++i) tot += a.T.slot_count[nbase + i];
-            A = __fmaf_rn((float)d, a_prior, (float)tot);
-          } else {
-            A = __fmul_rn((float)d, a_prior);
-          }
-          uint64_t picks = 0;  // 8 bits per ball
-          U4 r;
-          for (uint32_t b = 0; b < it.count; ++b) {
-            if ((b & 3u) == 0u) r = node_random(key, it.node_key, kStreamUrn, b >> 2);
-            uint32_t bits = (b & 3u) == 0u ? r.x : (b & 3u) == 1u ? r.y : (b & 3u) == 2u ? r.z : r.w;
-            uint32_t pick;
-            if (!(A > 0.0f)) {
-              // all parameters 0: the first ball is uniform, the rest follow it
-              pick = b == 0u ? uniform_below(bits, d) : (uint32_t)(picks & 0xFFu);
-            } else {
-              float u = __fmul_rn(u01f(bits), __fadd_rn(A, (float)b));
-              if (u >= A) {
-                uint32_t j = (uint32_t)__fadd_rn(u, -A);
-                if (j >= b) j = b - 1u;
-                pick = (uint32_t)(picks >> (8u * j)) & 0xFFu;
-              } else if (it.node >= 0) {
-                float acc = 0.0f;
-                pick = 0u;  // on fall-through (rounding): the last outcome with a positive parameter
-                for (uint32_t i = 0; i < d; ++i) {
-                  float al = __fadd_rn((float)a.T.slot_count[nbase + i], a_prior);
-                  acc = __fadd_rn(acc, al);
-                  if (al > 0.0f) pick = i;
-                  if (u < acc) break;
-                }
-              } else {
-                pick = (uint32_t)__fdividef(u, a_prior);
-                if (pick >= d) pick = d - 1u;
-              }
-            }
-            picks |= (uint64_t)pick << (8u * b);
-            col[pick] = __uint_as_float(__float_as_uint(col[pick]) + 1u);
-          }
-        }
-        // count what this item emits
-        for (uint32_t i = 0; i < K; ++i) {
-          if (__float_as_uint(col[i]) == 0u) continue;
-          if (leaf_children) ++n_ent; else ++n_child;
-        }
-        if (T && __float_as_uint(col[K]) != 0u) ++n_ent;
-      }
-
-      // ---- compaction: block-wide prefix sums give every thread its output ranges --------------
-      uint32_t tot;
-      uint32_t off = block_exclusive_scan<BLOCK>((n_ent << 16) | n_child, sm.warp_scan, &tot);
-      const uint32_t out_base = sm.n_out, ent_base = sm.n_entries;
-      const uint32_t tot_child = tot & 0xFFFFu, tot_ent = tot >> 16;
-      const bool overflow = (out_base + tot_child > a.cap_items) || (ent_base + tot_ent > a.cap_entries);
-      if (overflow) {
-        if (tid == 0) *a.error_flag = 1;
-      } else if (active) {
-        uint32_t co = out_base + (off & 0xFFFFu), eo = ent_base + (off >> 16);
-        const uint32_t nbase = sm.nbase[tid];
-        if (T) {
-          uint32_t c = __float_as_uint(col[K]);
-          if (c) {  // irv_node.cpp:128-132 / :63-68: ballots that stop at this node
-            sc.ent_key[eo] = it.prefix;
-            sc.ent_cnt[eo] = c;
-            sc.ent_len[eo] = (uint8_t)depth;
-            ++eo;
-          }
-        }
-        for (uint32_t i = 0; i < K; ++i) {
-          uint32_t c = __float_as_uint(col[i]);
-          if (c == 0u) continue;
-          uint32_t cand = it.node >= 0 ? (uint32_t)a.T.slot_cand[nbase + i] : nth_unused(it.used, nc, i);
-          BallotKey<W> pk = it.prefix;
-          key_set<W>(pk, (int)depth, cand);
-          if (leaf_children) {
-            sc.ent_key[eo] = pk;
-            sc.ent_cnt[eo] = c;
-            sc.ent_len[eo] = (uint8_t)(depth + 1);
-            ++eo;
-          } else {
-            Item<W> ch;
-            ch.prefix = pk;
-            ch.node_key = child_node_key(it.node_key, cand);
-            ch.count = c;
-            ch.node = it.node >= 0 ? a.T.slot_child[nbase + i] : -1;
-            ch.used = it.used | (1u << cand);
-            ch.pad_ = 0;
-            out[co++] = ch;
-          }
-        }
-      }
-      __syncthreads();
-      if (tid == 0 && !overflow) {
-        sm.n_out = out_base + tot_child;
-        sm.n_entries = ent_base + tot_ent;
-      }
-      __syncthreads();
+    if (tid == 0) {
+      sm.next_small = 0;
+      sm.next_big = 0;
+      sm.out_small = 0;
+      sm.out_big = 0;
     }
-    if (tid == 0) sm.n_in = leaf_children ? 0u : sm.n_out;
+    __syncthreads();
+    // Small items of this depth: one thread each, walked to completion (they never re-enter a queue).
+    for (;;) {
+      uint32_t start = 0;
+      if (lane == 0) start = atomicAdd(&sm.next_small, 32u);
+      start = __shfl_sync(0xffffffffu, start, 0);
+      if (start >= n_small) break;
+      if (start + lane < n_small) walk_small_item<W, BLOCK>(a, sc, sm, in[start + lane], depth, key, stat);
+      __syncwarp();
+    }
+    // Big items: warps claim chunks and run the Gamma / binomial-tree path.
+    int log_dp = 1;
+    while ((1u << log_dp) < lv.d) ++log_dp;
+    const uint32_t ci = min((uint32_t)C::kMaxItems, (uint32_t)C::kTileWords / (2u * (1u << log_dp) + 1u));
+    for (;;) {
+      uint32_t start = 0;
+      if (lane == 0) start = atomicAdd(&sm.next_big, ci);
+      start = __shfl_sync(0xffffffffu, start, 0);
+      if (start >= n_big) break;
+      const uint32_t m = min(ci, n_big - start);
+      // big items sit at in[cap-1], in[cap-2], ...: a chunk is the ascending range ending at cap-1-start
+      expand_chunk<W, BLOCK, LOG>(a, sc, sm, wt, in + (a.cap_items - start - m), m, lv, log_dp, out, key, stat);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      sm.n_small = lv.leaf_children ? 0u : sm.out_small;
+      sm.n_big = lv.leaf_children ? 0u : sm.out_big;
+      if (sm.overflow) *a.error_flag = 1;
+    }
     cur ^= 1;
     __syncthreads();
+    if (sm.overflow) break;
   }
+  if (tid == 0 && sm.n_entries > a.cap_entries) sm.n_entries = a.cap_entries;
+  __syncthreads();
 }
 
 // socialChoiceIRV (irv_ballot.cpp:42-138) for one election. Every entry carries its current
@@ -517,8 +382,8 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
 
 template <int W, int BLOCK, bool LOG>
 __global__ void __launch_bounds__(BLOCK) simulate_kernel(const __grid_constant__ SimArgs a) {
-  extern __shared__ __align__(16) float s_val[];
   __shared__ SharedFixed<BLOCK> sm;
+  __shared__ WarpTile<W> tiles[BLOCK / 32];
   const int tid = threadIdx.x;
   const uint32_t nc = a.P.nc;
   Scratch<W> sc;
@@ -536,8 +401,7 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const __grid_constant__
     if (e >= a.n_elections) break;
     const RngKey key = election_key(a.seed, a.first_election + e);
 
-    expand_election<W, BLOCK, LOG>(a, sc, sm, s_val, key, stat);
-    __syncthreads();
+    expand_election<W, BLOCK, LOG>(a, sc, sm, tiles, key, stat);
     if (tid == 0) {
       stat[kStatEntries] += sm.n_entries;
       if (a.entry_count_out) *a.entry_count_out = sm.n_entries;

@@ -252,21 +252,58 @@ def test_determinism_and_range_splitting(pkg, L):
         acc += ww
         parts.append(oo)
     assert acc.tolist() == w.tolist() and np.array_equal(np.vstack(parts), orders)
-    for bt in (32, 64, 128, 256):  # the launch shape must not matter either
-        t.tune(block_threads=bt)
-        w2, o2 = t.sample_posterior_counts(300, 2000, seed="SPLIT", return_orders=True)
-        assert w2.tolist() == w.tolist() and np.array_equal(o2, orders)
+    for mode in (0, 1):
+        for bt in (32, 64, 128, 256):  # neither the kernel nor its launch shape may matter
+            t.tune(block_threads=bt, mode=mode)
+            w2, o2 = t.sample_posterior_counts(300, 2000, seed="SPLIT", return_orders=True)
+            assert w2.tolist() == w.tolist() and np.array_equal(o2, orders)
     t.tune(block_threads=0)
     assert t.sample_posterior_counts(300, 2000, seed="OTHER").tolist() != w.tolist()
 
 
+@pytest.mark.parametrize("nc,mn,mx,a0,vd,n_obs,n_ballots,replace", [
+    (4, 0, 4, 1.0, False, 0, 1000, False), (6, 0, 6, 1.0, False, 300, 300, False),
+    (6, 0, 3, 1.0, False, 500, 3000, False), (9, 2, 5, 0.5, False, 800, 800, False),
+    (10, 0, 10, 1.0, False, 3000, 100_000, False), (5, 0, 5, 0.0, False, 40, 400, True),
+    (8, 7, 7, 1e-4, True, 100, 20_000, False), (20, 0, 20, 1.0, False, 500, 50_000, False),
+    (32, 0, 32, 1.0, False, 300, 5000, False), (14, 3, 9, 2.0, True, 200, 3000, True)])
+def test_deferred_equals_materialised(pkg, L, nc, mn, mx, a0, vd, n_obs, n_ballots, replace):
+    """mode=1 (expand a node only when IRV looks below it) and mode=0 (materialise every ballot, as the
+    reference does) must give the same elimination order for every election and the same win counts:
+    both evaluate the same counter-based draws. Includes observed ballots longer than max_depth, n_ballots
+    == n_observed (nothing sampled), an empty tree, a0 = 0 and every key width."""
+    pmf = np.ones(nc + 1)
+    pmf[:mn] = 0
+    t = pkg.dirichlet_tree(names(pkg, nc), mn, mx, a0, vd, device=0)
+    if n_obs:
+        prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.25, n_obs, nc + 77, pmf)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t.update_indices(prefs, offsets)
+    res = []
+    for mode in (0, 1):
+        t.tune(mode=mode)
+        for nw in (1, 2):
+            res.append((mode, nw) + t.sample_posterior_counts(400, n_ballots, n_winners=nw, replace=replace,
+                                                              seed="DEFER", return_orders=True))
+            res.append((mode, nw, t.sample_posterior_counts(400, n_ballots, n_winners=nw, replace=replace,
+                                                            seed="DEFER"), None))
+        assert t.last_stats()["mode"] == mode
+    half = len(res) // 2
+    for a, b in zip(res[:half], res[half:]):
+        assert a[1] == b[1] and a[2].tolist() == b[2].tolist()
+        assert (a[3] is None and b[3] is None) or np.array_equal(a[3], b[3])
+    assert res[0][2].tolist() == res[1][2].tolist()  # with and without the order output
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("nc,mn,mx,a0,vd,n_obs,n_ballots,replace", [
     (4, 0, 3, 1.0, False, 1000, 10_000, False), (6, 0, 5, 1.0, False, 300, 3000, False),
     (8, 7, 7, 0.01, True, 200, 5000, False), (10, 0, 10, 1.0, False, 2000, 20_000, False),
     (5, 0, 5, 0.0, False, 50, 500, False), (7, 2, 4, 3.0, False, 100, 1000, True),
     (16, 0, 16, 1.0, False, 400, 4000, False), (27, 1, 27, 0.5, True, 300, 2000, False)])
 def test_in_kernel_irv_bit_exact_vs_oracle_on_the_kernels_own_elections(pkg, L, port, nc, mn, mx, a0, vd, n_obs,
-                                                                        n_ballots, replace):
+                                                                        n_ballots, replace, mode):
     """sample_posterior's elimination orders vs socialChoiceIRV run by the oracle on exactly the ballots the
     kernel drew (dtree_posterior_set re-materialises election e). Covers the observed-ballot table, all
     key widths, a0 = 0 and the vd option."""
@@ -274,6 +311,7 @@ def test_in_kernel_irv_bit_exact_vs_oracle_on_the_kernels_own_elections(pkg, L, 
     pmf[:mn] = 0
     prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.3, n_obs, nc + 50, pmf)
     t, o = make_pair(pkg, port, nc, mn, mx, a0, vd, prefs, offsets)
+    t.tune(mode=mode)
     n_el = 24
     wins, orders = t.sample_posterior_counts(n_el, n_ballots, replace=replace, seed="OWN", return_orders=True)
     assert int(wins.sum()) == n_el
