@@ -217,3 +217,19 @@ def test_product_sources_never_touch_the_oracle(pkg):
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in src.replace("checked against the CPU oracle", ""), os.path.join(dp, f)
+
+
+def test_rcpp_shim_compiles_against_the_c_abi():
+    """INTEGRATION.md's Rcpp layer (elections.dtree_b200/host/r/R_tree_b200.cpp) is syntax-checked against
+    include/dtree_b200.h with a minimal Rcpp stand-in, since R is not installed in this image."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "tests", "stubs"),
+                        "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "elections.dtree_b200", "host", "r", "R_tree_b200.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
