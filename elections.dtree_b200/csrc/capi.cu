@@ -113,7 +113,7 @@ struct dtree {
   // device mirror
   uint64_t mirrored_version = ~0ull;
   FlatTree flat;
-  DevBuf<uint32_t> d_node_base, d_slot_count, d_obs_cnt, d_obs_tally0;
+  DevBuf<uint32_t> d_node_base, d_node_total, d_slot_count, d_obs_cnt, d_obs_tally0;
   DevBuf<int32_t> d_slot_child;
   DevBuf<uint8_t> d_slot_cand, d_obs_first;
   DevBuf<uint64_t> d_obs_key;
@@ -164,6 +164,7 @@ int ensure_mirror(dtree *t, cudaStream_t s) {
   const int W = key_words_for(nc);
   if (F.slot_count.size() >= 0xFFFFFFF0ull) return fail(DTREE_ERR_STATE, "tree has too many outcome slots for 32-bit indices");
   CUDA_TRY(t->d_node_base.upload(F.node_base, s));
+  CUDA_TRY(t->d_node_total.upload(F.node_total, s));
   CUDA_TRY(t->d_slot_count.upload(F.slot_count, s));
   CUDA_TRY(t->d_slot_child.upload(F.slot_child, s));
   CUDA_TRY(t->d_slot_cand.upload(F.slot_cand, s));
@@ -185,7 +186,7 @@ int ensure_mirror(dtree *t, cudaStream_t s) {
   CUDA_TRY(t->d_obs_first.upload(first, s));
   CUDA_TRY(t->d_obs_tally0.upload(tally0, s));
   t->n_obs_entries = (uint32_t)n;
-  t->stats[8] += (F.node_base.size() + F.slot_count.size() + F.slot_child.size()) * 4 + F.slot_cand.size() +
+  t->stats[8] += (F.node_base.size() + F.node_total.size() + F.slot_count.size() + F.slot_child.size()) * 4 + F.slot_cand.size() +
                  keys.size() * 8 + n * 5 + kMaxCandidates * 4;
   CUDA_TRY(cudaStreamSynchronize(s));  // the host vectors above die with this frame
   t->mirrored_version = t->tree.version();
@@ -195,7 +196,7 @@ int ensure_mirror(dtree *t, cudaStream_t s) {
 struct Plan {
   int W, block, grid, blocks_per_sm;
   bool log_gamma;
-  uint32_t cap_items, cap_entries;
+  uint32_t cap_items, cap_entries, cap_queue = 0, cap_big = 0;
   uint64_t stride;        // scratch bytes per block (materialising kernel) or per warp (deferred kernel)
   uint64_t stride_block;  // scratch bytes per block
   bool deferred = false;
@@ -270,10 +271,14 @@ int make_plan_deferred(dtree *t, uint32_t n_sample, uint32_t n_elections, Plan &
   if (t->blocks_per_sm > 0) occ = std::min(occ, t->blocks_per_sm);
   pl.blocks_per_sm = occ;
   const int wpb = pl.block / 32;
-  uint64_t worst = (uint64_t)n_sample + t->tree.n_nodes() + 1;
-  pl.cap_items = (uint32_t)std::min<uint64_t>(worst, 0xFFFFFFF0ull);
+  // A sampled ballot sits in at most one live node; a node with only observed ballots is a tree node.
+  uint64_t worst = (uint64_t)n_sample + t->tree.n_nodes() + 64;
+  if (worst > 0x7FFFFFF0ull) return fail(DTREE_ERR_ARG, "n_ballots too large for the deferred kernel; use mode 0");
+  pl.cap_items = (uint32_t)worst;
   pl.cap_entries = 0;
-  pl.stride = ((uint64_t)3 * pl.cap_items * sizeof(Item<1>) + 255) & ~255ull;  // per warp
+  pl.cap_queue = (uint32_t)worst;
+  pl.cap_big = (uint32_t)((uint64_t)n_sample / (t->urn_max + 1) + 64);
+  pl.stride = (deferred_scratch_bytes(pl.cap_items, pl.cap_queue, pl.cap_big) + 255) & ~255ull;  // per warp
   uint64_t grid = std::min<uint64_t>((uint64_t)occ * t->sm_count, ((uint64_t)n_elections + wpb - 1) / wpb);
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -289,6 +294,7 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
   memset(&a, 0, sizeof a);
   a.P = device_params(t->tree.P);
   a.T.node_base = t->d_node_base.p;
+  a.T.node_total = t->d_node_total.p;
   a.T.slot_count = t->d_slot_count.p;
   a.T.slot_child = t->d_slot_child.p;
   a.T.slot_cand = t->d_slot_cand.p;
@@ -298,6 +304,8 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
   a.scratch_stride = pl.stride;
   a.cap_items = pl.cap_items;
   a.cap_entries = pl.cap_entries;
+  a.cap_queue = pl.cap_queue;
+  a.cap_big = pl.cap_big;
   a.work_counter = t->d_counter.p;
   a.error_flag = t->d_error.p;
   a.stats = t->d_stats.p;
@@ -514,7 +522,7 @@ int dtree_destroy(dtree_t *t) {
   if (!t) return DTREE_OK;
   if (t->sm_count) {
     DeviceGuard g(t->device);
-    t->d_node_base.release(); t->d_slot_count.release(); t->d_obs_cnt.release(); t->d_obs_tally0.release();
+    t->d_node_base.release(); t->d_node_total.release(); t->d_slot_count.release(); t->d_obs_cnt.release(); t->d_obs_tally0.release();
     t->d_slot_child.release(); t->d_slot_cand.release(); t->d_obs_first.release(); t->d_obs_key.release();
     t->d_scratch.release(); t->d_wins.release(); t->d_stats.release(); t->d_counter.release(); t->d_error.release();
     t->d_entry_count.release(); t->d_orders.release();

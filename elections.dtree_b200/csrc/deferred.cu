@@ -19,6 +19,10 @@ cudaError_t launch_deferred(const SimArgs &a, const LaunchCfg &cfg) {
   }
 }
 
+uint64_t deferred_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t cap_big) {
+  return DeferredScratch::bytes(cap_items, cap_queue, cap_big);
+}
+
 template <int BLOCK, bool LOG>
 static int occ_d() {
   int n = 0;

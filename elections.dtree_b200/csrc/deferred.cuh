@@ -13,7 +13,7 @@
 // the tallies seen by every elimination round are the same integers, and so are the tie-breaks:
 // elimination orders and win counts are bit-identical to the materialising kernel's
 // (tests/test_gpu_parity.py::test_deferred_equals_materialised). The nodes never asked about —
-// typically everything below the two finalists' first preferences, i.e. most of the tree — are never
+// typically everything below the finalists' first preferences, i.e. most of the tree — are never
 // drawn, which removes most of the work of IRVNode::sample (irv_node.cpp:107-174) and all of the
 // list traffic of socialChoiceIRV (irv_ballot.cpp:42-138).
 //
@@ -21,6 +21,8 @@
 // observed counts ARE its slot counts, so they ride along with the sampled counts of each child.
 //
 // One warp per election; a block is a bundle of independent warps (no block barrier in the loop).
+// Nodes with a small sampled count are split one lane per node; big counts go through the
+// shared-memory tile path of split.cuh.
 #pragma once
 #include <cstdint>
 
@@ -28,91 +30,220 @@
 
 namespace dtb {
 
-typedef Item<1> DItem;  // prefix unused; pad_ = depth | holder << 8
+typedef Item<1> DItem;  // prefix unused; pad_ = depth
 
 struct DeferredWarp {
   uint32_t tally[kMaxCandidates];
-  uint32_t n_pending, n_out, overflow, pad;
+  uint32_t n_pool;    // high-water mark of the parked-node pool
+  int32_t n_free;     // free-list depth (may dip below 0 while lanes race for the last free slots)
+  uint32_t q_tail;    // small-count work queue (circular, monotone counters; q_head is a register)
+  uint32_t big_tail;  // big-count list being filled
+  uint32_t overflow;
 };
 
-// Splits the nodes in `in` and routes their children; repeats on the children whose candidate is
-// already eliminated until none are left. Returns with every live node parked in `pend`.
+// Per-warp scratch. Parked nodes live in `pool` (slot reuse through `free_list`), with the candidate they
+// are parked under in `holder` (0xFF = free slot). Nodes being split in the current round are transient:
+// small counts go through the circular `queue`, big counts through the ping-pong `big` lists.
+// Capacities are exact bounds: a sampled ballot is in at most one live node, and a node carrying only
+// observed ballots is one of the tree's nodes.
+struct DeferredScratch {
+  DItem *pool;
+  uint8_t *holder;
+  uint32_t *free_list;
+  DItem *queue;
+  DItem *big[2];
+  __host__ __device__ static uint64_t a16(uint64_t x) { return (x + 15) & ~15ull; }
+  __host__ __device__ static uint64_t bytes(uint32_t cap, uint32_t capq, uint32_t capb) {
+    return (uint64_t)cap * sizeof(DItem) + a16(cap) + a16((uint64_t)cap * 4) + (uint64_t)capq * sizeof(DItem) +
+           2 * (uint64_t)capb * sizeof(DItem);
+  }
+  __device__ void bind(uint8_t *p, uint32_t cap, uint32_t capq, uint32_t capb) {
+    pool = (DItem *)p; p += (uint64_t)cap * sizeof(DItem);
+    holder = p; p += a16(cap);
+    free_list = (uint32_t *)p; p += a16((uint64_t)cap * 4);
+    queue = (DItem *)p; p += (uint64_t)capq * sizeof(DItem);
+    big[0] = (DItem *)p; p += (uint64_t)capb * sizeof(DItem);
+    big[1] = (DItem *)p;
+  }
+};
+
+// Puts a node that must be split in the current round on the right transient list.
+__device__ __forceinline__ void enqueue_node(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
+                                             const DItem &ch, int big_sel) {
+  if (ch.count > a.urn_max) {
+    const uint32_t q = coalesced_reserve(&ws.big_tail);
+    if (q < a.cap_big) sc.big[big_sel][q] = ch;
+    else ws.overflow = 1;
+  } else {
+    const uint32_t q = coalesced_reserve(&ws.q_tail);
+    sc.queue[q % a.cap_queue] = ch;
+  }
+}
+
+// Routes the ballots of one child of a node that has just been split. May be called by any subset of
+// lanes (divergent code). `tot` ballots now have `cand` as their next preference; `cs` of them are
+// sampled ballots that continue below the child, `child` is the child's CSR node (-1: none).
+__device__ __forceinline__ void route_child(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
+                                            const DItem &x, uint32_t depth, uint32_t eliminated, uint32_t cand,
+                                            uint32_t tot, uint32_t cs, int32_t child, bool has_obs, int big_sel) {
+  const bool standing = !(eliminated >> cand & 1u);
+  if (standing) atomicAdd(&ws.tally[cand], tot);
+  const bool cont = cs > 0u || (has_obs && child >= 0);
+  if (!cont) return;  // these ballots end with `cand`: they exhaust when it is eliminated
+  DItem ch;
+  ch.prefix.w[0] = 0;
+  ch.node_key = child_node_key(x.node_key, cand);
+  ch.count = cs;
+  ch.node = child;
+  ch.used = x.used | (1u << cand);
+  ch.pad_ = depth + 1u;
+  if (!standing) {  // its candidate is already out: split it in this round as well
+    enqueue_node(a, ws, sc, ch, big_sel);
+    return;
+  }
+  // park it under `cand`: reuse a freed pool slot if there is one, else grow the pool
+  const uint32_t m = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  const int k = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+  int old_free = 0;
+  if (lane == leader) old_free = atomicSub(&ws.n_free, k);
+  old_free = __shfl_sync(m, old_free, leader);
+  const int from_free = max(0, min(k, old_free));  // lanes of rank < from_free get a recycled slot
+  uint32_t grow_base = 0;
+  if (lane == leader && k > from_free) grow_base = atomicAdd(&ws.n_pool, (uint32_t)(k - from_free));
+  grow_base = __shfl_sync(m, grow_base, leader);
+  uint32_t j;
+  if (rank < from_free) j = sc.free_list[old_free - 1 - rank];
+  else j = grow_base + (uint32_t)(rank - from_free);
+  if (j >= a.cap_items) {
+    ws.overflow = 1;
+    return;
+  }
+  sc.pool[j] = ch;
+  sc.holder[j] = (uint8_t)cand;
+}
+
+// One lane splits one node with a small sampled count (0..urn_max) and routes its children.
+__device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
+                                                 const DItem &x, uint32_t eliminated, const RngKey key, int big_sel,
+                                                 uint32_t *stat) {
+  const uint32_t nc = a.P.nc;
+  const uint32_t depth = x.pad_ & 0xFFu;
+  const LevelInfo lv = level_info(a.P, depth);
+  const uint32_t nb = x.node >= 0 ? a.T.node_base[x.node] : 0xFFFFFFFFu;
+  stat[kStatItems] += 1;
+  stat[kStatUrnItems] += 1;
+  const uint64_t picks = x.count ? urn_picks(a, lv, x.node, nb, x.count, key, x.node_key) : 0ull;
+  if (nb != 0xFFFFFFFFu && a.use_obs) {
+    // initialised node carrying observed ballots: every child slot may have something to route
+    uint64_t c4[2] = {0ull, 0ull};  // 4-bit count per slot (count <= 8)
+    for (uint32_t b = 0; b < x.count; ++b) {
+      const uint32_t s = (uint32_t)(picks >> (8u * b)) & 0xFFu;
+      if (s == lv.K) continue;  // the ballot stops here: exhausted
+      c4[s >> 4] += 1ull << (4u * (s & 15u));
+    }
+    stat[kStatSlots] += lv.d;
+    for (uint32_t slot = 0; slot < lv.K; ++slot) {
+      const uint32_t c = (uint32_t)(c4[slot >> 4] >> (4u * (slot & 15u))) & 15u;
+      const uint32_t obs = a.T.slot_count[nb + slot];
+      if (c + obs == 0u) continue;
+      route_child(a, ws, sc, x, depth, eliminated, a.T.slot_cand[nb + slot], c + obs, lv.leaf_children ? 0u : c,
+                  a.T.slot_child[nb + slot], obs > 0u, big_sel);
+    }
+  } else {
+    // prior-only subtree (or sampling with replacement): only the drawn outcomes matter
+    uint32_t done = 0;
+    for (uint32_t b = 0; b < x.count; ++b) {
+      if (done >> b & 1u) continue;
+      const uint32_t slot = (uint32_t)(picks >> (8u * b)) & 0xFFu;
+      uint32_t c = 1;
+      for (uint32_t b2 = b + 1; b2 < x.count; ++b2)
+        if (((uint32_t)(picks >> (8u * b2)) & 0xFFu) == slot) {
+          ++c;
+          done |= 1u << b2;
+        }
+      if (slot == lv.K) continue;  // the ballots stop here: exhausted
+      const uint32_t cand = nb != 0xFFFFFFFFu ? (uint32_t)a.T.slot_cand[nb + slot] : nth_unused(x.used, nc, slot);
+      const int32_t child = nb != 0xFFFFFFFFu ? a.T.slot_child[nb + slot] : -1;
+      route_child(a, ws, sc, x, depth, eliminated, cand, c, lv.leaf_children ? 0u : c, child, false, big_sel);
+    }
+  }
+}
+
+// The warp splits a list of nodes with big sampled counts through the shared-memory tile.
 template <bool LOG>
-__device__ void deferred_cascade(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, DItem *in, DItem *out,
-                                 uint32_t n_in, DItem *pend, const uint32_t eliminated, const int log_dp_max,
-                                 const RngKey key, uint32_t *stat) {
+__device__ void split_big_nodes(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
+                                const DItem *list, uint32_t n_list, uint32_t eliminated, int log_dp_max,
+                                const RngKey key, int big_sel, uint32_t *stat) {
   const int lane = threadIdx.x & 31;
-  const uint32_t nc = a.P.nc, cap = a.cap_items;
+  const uint32_t nc = a.P.nc;
   const uint32_t dp_max = 1u << log_dp_max, stride = 2u * dp_max + 1u;
   const uint32_t ci = min((uint32_t)Chunk<1>::kMaxItems, (uint32_t)Chunk<1>::kTileWords / stride);
-  while (n_in > 0) {
-    if (lane == 0) ws.n_out = 0;
-    __syncwarp();
-    for (uint32_t start = 0; start < n_in; start += ci) {
-      const uint32_t m = min(ci, n_in - start);
-      for (uint32_t it = lane; it < m; it += 32) {
-        DItem x = in[start + it];
-        wt.item[it] = x;
-        wt.nbase[it] = x.node >= 0 ? a.T.node_base[x.node] : 0xFFFFFFFFu;
-        stat[kStatItems] += 1;
-      }
-      __syncwarp();
-      split_items<1, LOG>(a, wt, m, log_dp_max, key, stat);
-      for (uint32_t base = 0; base < (m << log_dp_max); base += 32) {
-        const uint32_t p = base + lane;
-        const uint32_t it = p >> log_dp_max, slot = p & (dp_max - 1u);
-        bool live = false, standing = false, cont = false;
-        uint32_t tot = 0, cand = 0, cs = 0, depth = 0;
-        int32_t child = -1;
-        if (it < m) {
-          const DItem &x = wt.item[it];
-          depth = x.pad_ & 0xFFu;
-          const LevelInfo lv = level_info(a.P, depth);
-          if (slot < lv.K) {  // the stop outcome (slot K) exhausts its ballots: nothing to route
-            const uint32_t nb = wt.nbase[it];
-            const uint32_t c = x.count ? wt.val[it * stride + (1u << tree_log2(lv.d)) + slot] : 0u;
-            uint32_t obs = 0;
-            if (nb != 0xFFFFFFFFu) {
-              if (a.use_obs) obs = a.T.slot_count[nb + slot];
-              cand = a.T.slot_cand[nb + slot];
-              child = a.T.slot_child[nb + slot];
-            } else {
-              cand = nth_unused(x.used, nc, slot);
-            }
-            tot = c + obs;
-            cs = lv.leaf_children ? 0u : c;  // sampled ballots end with this preference at the last level
-            cont = cs > 0u || (a.use_obs && child >= 0 && obs > 0u);
-            live = tot > 0u;
-            standing = !(eliminated >> cand & 1u);
-          }
-        }
-        warp_tally_add(ws.tally, live && standing, cand, tot);
-        const uint32_t po = warp_reserve(&ws.n_pending, live && standing && cont, lane);
-        const uint32_t fo = warp_reserve(&ws.n_out, live && !standing && cont, lane);
-        if (!(live && cont)) continue;
-        const DItem &x = wt.item[it];
-        DItem ch;
-        ch.prefix.w[0] = 0;
-        ch.node_key = child_node_key(x.node_key, cand);
-        ch.count = cs;
-        ch.node = child;
-        ch.used = x.used | (1u << cand);
-        ch.pad_ = (depth + 1u) | (cand << 8);
-        const uint32_t pos = standing ? po : fo;
-        if (pos < cap) {
-          (standing ? pend : out)[pos] = ch;
-        } else {
-          ws.overflow = 1;
-        }
-      }
-      __syncwarp();
+  for (uint32_t start = 0; start < n_list; start += ci) {
+    const uint32_t m = min(ci, n_list - start);
+    for (uint32_t it = lane; it < m; it += 32) {
+      DItem x = list[start + it];
+      wt.item[it] = x;
+      wt.nbase[it] = x.node >= 0 ? a.T.node_base[x.node] : 0xFFFFFFFFu;
+      stat[kStatItems] += 1;
+      if (x.node >= 0) stat[kStatSlots] += level_info(a.P, x.pad_ & 0xFFu).d;
     }
     __syncwarp();
-    n_in = min(ws.n_out, cap);
-    DItem *t = in;
-    in = out;
-    out = t;
+    split_items<1, LOG>(a, wt, m, log_dp_max, key, stat);
+    for (uint32_t p = lane; p < (m << log_dp_max); p += 32) {
+      const uint32_t it = p >> log_dp_max, slot = p & (dp_max - 1u);
+      const DItem &x = wt.item[it];
+      const uint32_t depth = x.pad_ & 0xFFu;
+      const LevelInfo lv = level_info(a.P, depth);
+      if (slot >= lv.K) continue;  // padding, or the stop outcome (its ballots are exhausted)
+      const uint32_t nb = wt.nbase[it];
+      const uint32_t c = wt.val[it * stride + (1u << tree_log2(lv.d)) + slot];
+      uint32_t obs = 0, cand;
+      int32_t child = -1;
+      if (nb != 0xFFFFFFFFu) {
+        if (a.use_obs) obs = a.T.slot_count[nb + slot];
+        cand = a.T.slot_cand[nb + slot];
+        child = a.T.slot_child[nb + slot];
+      } else {
+        cand = nth_unused(x.used, nc, slot);
+      }
+      if (c + obs == 0u) continue;
+      route_child(a, ws, sc, x, depth, eliminated, cand, c + obs, lv.leaf_children ? 0u : c, child, obs > 0u, big_sel);
+    }
+    __syncwarp();
   }
+}
+
+// Splits everything that is queued, and whatever that enqueues, until nothing is left.
+template <bool LOG>
+__device__ void deferred_drain(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
+                               uint32_t &q_head, uint32_t eliminated, int log_dp_max, const RngKey key,
+                               uint32_t *stat) {
+  const int lane = threadIdx.x & 31;
+  int sel = 0;  // big[sel] is being filled
+  for (;;) {
+    // small counts: 32 nodes at a time, one lane each; their eliminated-candidate children rejoin the queue
+    for (;;) {
+      __syncwarp();
+      const uint32_t tail = ws.q_tail;
+      if (q_head >= tail) break;
+      const uint32_t i = q_head + lane;
+      q_head = min(q_head + 32u, tail);
+      if (i < tail) {
+        const DItem x = sc.queue[i % a.cap_queue];
+        split_small_node(a, ws, sc, x, eliminated, key, sel, stat);
+      }
+    }
+    __syncwarp();
+    const uint32_t n_big = min(ws.big_tail, a.cap_big);
+    if (n_big == 0) break;
+    __syncwarp();
+    if (lane == 0) ws.big_tail = 0;
+    __syncwarp();
+    split_big_nodes<LOG>(a, wt, ws, sc, sc.big[sel], n_big, eliminated, log_dp_max, key, sel ^ 1, stat);
+    sel ^= 1;
+  }
+  __syncwarp();
 }
 
 template <int BLOCK, bool LOG>
@@ -125,8 +256,8 @@ __global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__
   const uint32_t cand_mask = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u);
   WarpTile<1> &wt = tiles[warp];
   DeferredWarp &ws = wstate[warp];
-  DItem *pend = (DItem *)(a.scratch + ((uint64_t)blockIdx.x * (BLOCK / 32) + warp) * a.scratch_stride);
-  DItem *fa = pend + cap, *fb = fa + cap;
+  DeferredScratch sc;
+  sc.bind(a.scratch + ((uint64_t)blockIdx.x * (BLOCK / 32) + warp) * a.scratch_stride, cap, a.cap_queue, a.cap_big);
   const int log_dp_max = tree_log2(level_info(a.P, 0).d);
   uint32_t stat[kStatCount];
 #pragma unroll
@@ -144,8 +275,6 @@ __global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__
 
     ws.tally[lane] = 0;
     if (lane == 0) {
-      ws.n_pending = 0;
-      ws.overflow = 0;
       DItem root;
       root.prefix.w[0] = 0;
       root.node_key = kRootNodeKey;
@@ -153,11 +282,22 @@ __global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__
       root.node = 0;
       root.used = 0;
       root.pad_ = 0;
-      fa[0] = root;
+      ws.n_pool = 0;
+      ws.n_free = 0;
+      ws.overflow = 0;
+      ws.q_tail = 0;
+      ws.big_tail = 0;
+      if (a.n_sample > a.urn_max) {
+        sc.big[0][0] = root;
+        ws.big_tail = 1;
+      } else {
+        sc.queue[0] = root;
+        ws.q_tail = 1;
+      }
     }
     __syncwarp();
-    uint32_t eliminated = 0, tie_rounds = 0, my_order = 0xFFu;
-    deferred_cascade<LOG>(a, wt, ws, fa, fb, 1u, pend, eliminated, log_dp_max, key, stat);
+    uint32_t eliminated = 0, tie_rounds = 0, my_order = 0xFFu, q_head = 0;
+    deferred_drain<LOG>(a, wt, ws, sc, q_head, eliminated, log_dp_max, key, stat);
 
     for (uint32_t round = 0; round < n_rounds; ++round) {
       // candidates with the minimal tally among those standing (irv_ballot.cpp:88-98), one lane each
@@ -175,29 +315,38 @@ __global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__
       const uint32_t chosen = (uint32_t)__ffs(tied) - 1u;
       if (lane == (int)round) my_order = chosen;
       eliminated |= 1u << chosen;
-      // pull the nodes parked under the eliminated candidate; keep the rest, compacted in place
-      const uint32_t np = min(ws.n_pending, cap);
-      uint32_t kept = 0, n_in = 0;
-      for (uint32_t base = 0; base < np; base += 32) {
-        const uint32_t i = base + lane;
-        DItem x;
-        bool mine = false, keep = false;
-        if (i < np) {
-          x = pend[i];
-          mine = ((x.pad_ >> 8) & 0xFFu) == chosen;
-          keep = !mine;
-        }
-        __syncwarp();  // every lane has read its slot before any lane overwrites one
-        const uint32_t mm = __ballot_sync(0xffffffffu, mine), mk = __ballot_sync(0xffffffffu, keep);
-        const uint32_t lt = (1u << lane) - 1u;
-        if (mine) fa[n_in + __popc(mm & lt)] = x;
-        if (keep) pend[kept + __popc(mk & lt)] = x;
-        n_in += __popc(mm);
-        kept += __popc(mk);
-      }
-      if (lane == 0) ws.n_pending = kept;
+      if (mn == 0u) continue;  // nobody counts for this candidate: nothing is parked under it
+      // queue the nodes parked under the eliminated candidate: scan the holder bytes 16 per lane
+      if (lane == 0 && ws.n_free < 0) ws.n_free = 0;
       __syncwarp();
-      if (n_in) deferred_cascade<LOG>(a, wt, ws, fa, fb, n_in, pend, eliminated, log_dp_max, key, stat);
+      const uint32_t np = min(ws.n_pool, cap);
+      const uint32_t n_vec = (np + 15u) / 16u;
+      const uint32_t pattern = chosen * 0x01010101u;
+      for (uint32_t vbase = 0; vbase < n_vec; vbase += 32) {
+        const uint32_t v = vbase + lane;
+        uint32_t hits = 0;
+        if (v < n_vec) {
+          const uint4 h = reinterpret_cast<const uint4 *>(sc.holder)[v];
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t eq = __vcmpeq4(hw[q], pattern);
+            hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * q);
+          }
+        }
+        while (hits) {
+          const uint32_t j = v * 16u + (uint32_t)__ffs(hits) - 1u;
+          hits &= hits - 1u;
+          if (j >= np) break;
+          sc.holder[j] = 0xFF;
+          const DItem x = sc.pool[j];
+          enqueue_node(a, ws, sc, x, 0);
+          const uint32_t f = coalesced_reserve(reinterpret_cast<uint32_t *>(&ws.n_free));
+          sc.free_list[f] = j;
+        }
+      }
+      __syncwarp();
+      deferred_drain<LOG>(a, wt, ws, sc, q_head, eliminated, log_dp_max, key, stat);
     }
 
     if (ws.overflow) {

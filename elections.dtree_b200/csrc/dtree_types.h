@@ -49,6 +49,7 @@ struct DeviceParams {
 // "ballot stops here" slot. Nodes of one depth are contiguous; siblings are adjacent.
 struct DeviceTree {
   const uint32_t *node_base;   // [n_nodes + 1]
+  const uint32_t *node_total;  // [n_nodes] sum of the node's K child-slot counts (stop slot excluded)
   const uint32_t *slot_count;  // observed counts (IRVNode::as)
   const int32_t *slot_child;   // child node id, -1 = uninitialised (IRVNode::children) / stop slot
   const uint8_t *slot_cand;    // candidate of the slot (path-dependent, irv_node.cpp:219), 0xFF = stop slot

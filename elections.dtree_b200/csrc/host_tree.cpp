@@ -146,6 +146,9 @@ void HostTree::flatten(FlatTree &F) const {
           F.slot_child.push_back(-1);
         }
       }
+      uint32_t child_total = 0;
+      for (uint32_t j = 0; j < K; ++j) child_total += counts_[base + j];
+      F.node_total.push_back(child_total);
       F.node_depth.push_back((uint8_t)depth);
       F.node_parent_slot.push_back(q.parent_slot);
       F.node_base.push_back((uint32_t)F.slot_count.size());

@@ -21,6 +21,7 @@ struct HostParams {
 // CSR image of the trie, ready for upload, plus what the exports need.
 struct FlatTree {
   std::vector<uint32_t> node_base;
+  std::vector<uint32_t> node_total;  // per node: sum of its child-slot counts
   std::vector<uint32_t> slot_count;
   std::vector<int32_t> slot_child;
   std::vector<uint8_t> slot_cand;

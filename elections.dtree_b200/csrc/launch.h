@@ -29,6 +29,7 @@ int simulate_blocks_per_sm(uint32_t nc, int block, bool log_gamma);
 // deferred_kernel (deferred.cuh): one warp per election, `block` threads per block (64, 128 or 256).
 cudaError_t launch_deferred(const SimArgs &a, const LaunchCfg &cfg);
 int deferred_blocks_per_sm(int block, bool log_gamma);
+uint64_t deferred_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t cap_big);  // per warp
 
 // Stand-alone IRV over entries already placed in block 0's scratch (dtree_irv).
 struct IrvArgs {

@@ -66,30 +66,49 @@ struct SharedFixed {
   uint8_t order[kMaxCandidates];
 };
 
-// One thread finishes the whole subtree below a small item (count <= urn_max <= 8): a depth-first
-// walk with an explicit stack of at most 8 frames (every frame holds >= 1 of the <= 8 ballots),
-// applying the urn at each node and emitting finished ballots straight into the entry list.
-// The draws at a node depend only on (election, node), so this gives the same ballots as pushing
+// Small items (count <= urn_max <= 8): each lane finishes whole subtrees on its own, depth-first with
+// an explicit stack of at most 8 frames (every frame holds >= 1 of the <= 8 ballots), applying the urn at
+// each node and emitting finished ballots straight into the entry list. A lane whose stack runs empty
+// claims the next item of the queue, so the warp keeps all lanes on the same loop body until the queue is
+// drained. The draws at a node depend only on (election, node), so this gives the same ballots as pushing
 // the item through the level-synchronous queue would.
 template <int W, int BLOCK>
-__device__ void walk_small_item(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, const Item<W> &root,
-                                uint32_t root_depth, const RngKey key, uint32_t *stat) {
+__device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, const Item<W> *in,
+                                 uint32_t n_small, uint32_t root_depth, const RngKey key, uint32_t *stat) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nc = a.P.nc;
   Item<W> stack[8];
   int top = 0;
-  stack[0] = root;
-  stack[0].pad_ = root_depth;
-  top = 1;
-  const uint32_t nc = a.P.nc;
-  while (top > 0) {
-    Item<W> f = stack[--top];
+  bool drained = false;
+  for (;;) {
+    const bool need = top == 0 && !drained;
+    const uint32_t mask = __ballot_sync(0xffffffffu, need);
+    if (mask) {
+      const int leader = __ffs(mask) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&sm.next_small, (uint32_t)__popc(mask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (need) {
+        const uint32_t idx = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        if (idx < n_small) {
+          stack[0] = in[idx];
+          stack[0].pad_ = root_depth;
+          top = 1;
+        } else {
+          drained = true;
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, top > 0)) break;
+    if (top == 0) continue;
+    const Item<W> f = stack[--top];
     const LevelInfo lv = level_info(a.P, f.pad_);
     const uint32_t nbase = f.node >= 0 ? a.T.node_base[f.node] : 0xFFFFFFFFu;
     stat[kStatItems] += 1;
     stat[kStatUrnItems] += 1;
     if (f.node >= 0) stat[kStatSlots] += lv.d;
-    const uint64_t picks = urn_picks(a, lv, nbase, f.count, key, f.node_key);
-    // group equal outcomes
-    uint32_t done = 0;  // bit b set: ball b already accounted for
+    const uint64_t picks = urn_picks(a, lv, f.node, nbase, f.count, key, f.node_key);
+    uint32_t done = 0;  // bit b set: ball b already grouped with an earlier ball of the same outcome
     for (uint32_t b = 0; b < f.count; ++b) {
       if (done >> b & 1u) continue;
       const uint32_t slot = (uint32_t)(picks >> (8u * b)) & 0xFFu;
@@ -252,15 +271,8 @@ __device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BL
       sm.out_big = 0;
     }
     __syncthreads();
-    // Small items of this depth: one thread each, walked to completion (they never re-enter a queue).
-    for (;;) {
-      uint32_t start = 0;
-      if (lane == 0) start = atomicAdd(&sm.next_small, 32u);
-      start = __shfl_sync(0xffffffffu, start, 0);
-      if (start >= n_small) break;
-      if (start + lane < n_small) walk_small_item<W, BLOCK>(a, sc, sm, in[start + lane], depth, key, stat);
-      __syncwarp();
-    }
+    // Small items of this depth are walked to completion (they never re-enter a queue).
+    if (n_small) walk_small_items<W, BLOCK>(a, sc, sm, in, n_small, depth, key, stat);
     // Big items: warps claim chunks and run the Gamma / binomial-tree path.
     int log_dp = 1;
     while ((1u << log_dp) < lv.d) ++log_dp;
@@ -349,32 +361,51 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
     const bool any = sm.tally[chosen] != 0u;
     __syncthreads();
     if (!any) continue;  // nobody holds ballots for this candidate: nothing to redistribute
-    // redistribution (irv_ballot.cpp:109-133)
-    const uint32_t n_tot = n_ent + n_obs;
-    for (uint32_t base = 0; base < n_tot; base += BLOCK) {
-      uint32_t i = base + tid;
-      bool valid = false;
-      uint32_t cand = 0, cnt = 0;
-      if (i < n_ent) {
-        if (sc.ent_holder[i] == chosen) {
-          cand = first_standing<W>(sc.ent_key[i], sc.ent_len[i], eliminated);
-          sc.ent_holder[i] = (uint8_t)cand;
-          cnt = sc.ent_cnt[i];
-          valid = cand != 0xFFu;
-          stat[kStatRereads] += 1;
+    // redistribution (irv_ballot.cpp:109-133): scan the holder bytes 16 at a time; only the entries
+    // held by the eliminated candidate are re-examined
+    const uint32_t pattern = chosen * 0x01010101u;
+    for (int part = 0; part < 2; ++part) {
+      uint8_t *holder = part == 0 ? sc.ent_holder : sc.obs_holder;
+      const uint32_t n_part = part == 0 ? n_ent : n_obs;
+      const uint32_t n_vec = (n_part + 15u) / 16u;
+      for (uint32_t vbase = 0; vbase < n_vec; vbase += BLOCK) {
+        const uint32_t v = vbase + tid;
+        uint32_t hw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (v < n_vec) {
+          const uint4 h = reinterpret_cast<const uint4 *>(holder)[v];
+          hw[0] = h.x; hw[1] = h.y; hw[2] = h.z; hw[3] = h.w;
         }
-      } else if (i < n_tot) {
-        uint32_t j = i - n_ent;
-        if (sc.obs_holder[j] == chosen) {
-          // an observed key stores at most nc-1 preferences; its length is implied by repetition
-          cand = first_standing<W>(obs_key[j], nc - 1, eliminated);
-          sc.obs_holder[j] = (uint8_t)cand;
-          cnt = a.obs_cnt[j];
-          valid = cand != 0xFFu;
-          stat[kStatRereads] += 1;
+        // a matching byte is rare; the warp goes through its hits together
+        uint32_t hits = 0;  // bit j: byte j of this lane's 16 equals `chosen`
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t eq = __vcmpeq4(hw[q], pattern);  // 0xFF per equal byte
+          hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * q);
+        }
+        while (__any_sync(0xffffffffu, hits != 0u)) {
+          bool valid = false;
+          uint32_t cand = 0, cnt = 0;
+          if (hits) {
+            const uint32_t j = (uint32_t)__ffs(hits) - 1u;
+            hits &= hits - 1u;
+            const uint32_t i = v * 16u + j;
+            if (i < n_part) {
+              if (part == 0) {
+                cand = first_standing<W>(sc.ent_key[i], sc.ent_len[i], eliminated);
+                cnt = sc.ent_cnt[i];
+              } else {
+                // an observed key stores at most nc-1 preferences; its length is implied by repetition
+                cand = first_standing<W>(obs_key[i], nc - 1, eliminated);
+                cnt = a.obs_cnt[i];
+              }
+              holder[i] = (uint8_t)cand;
+              valid = cand != 0xFFu;
+              stat[kStatRereads] += 1;
+            }
+          }
+          warp_tally_add(sm.tally, valid, cand, cnt);
         }
       }
-      warp_tally_add(sm.tally, valid, cand, cnt);
     }
     __syncthreads();
   }

@@ -51,6 +51,7 @@ struct SimArgs {
   uint64_t scratch_stride;    // bytes per block
   uint32_t cap_items;         // frontier capacity (items) per buffer
   uint32_t cap_entries;
+  uint32_t cap_queue, cap_big; // deferred kernel: circular work queue / big-count lists (items)
   // outputs
   unsigned long long *win_counts;  // [nc], added to
   uint8_t *elim_orders;            // NULL or [n_elections * nc]
@@ -154,13 +155,13 @@ __device__ __forceinline__ uint32_t coalesced_reserve(uint32_t *cursor) {
 // probability b / (A + b), else draws a fresh outcome with probability alpha_i / A. Exactly
 // Dirichlet-multinomial(count, alpha); no Gamma or binomial variates. Returns the outcome of
 // ball b in bits [8b, 8b+8).
-__device__ __forceinline__ uint64_t urn_picks(const SimArgs &a, const LevelInfo &lv, uint32_t nbase, uint32_t count,
-                                              const RngKey key, uint64_t node_key) {
+__device__ __forceinline__ uint64_t urn_picks(const SimArgs &a, const LevelInfo &lv, int32_t node, uint32_t nbase,
+                                              uint32_t count, const RngKey key, uint64_t node_key) {
   const uint32_t d = lv.d;
   float A;
   if (nbase != 0xFFFFFFFFu) {
-    uint32_t tot = 0;
-    for (uint32_t i = 0; i < d; ++i) tot += a.T.slot_count[nbase + i];
+    uint32_t tot = a.T.node_total[node];
+    if (lv.T) tot += a.T.slot_count[nbase + lv.K];
     A = __fmaf_rn((float)d, lv.a_prior, (float)tot);
   } else {
     A = __fmul_rn((float)d, lv.a_prior);
@@ -313,7 +314,7 @@ __device__ void split_items(const SimArgs &a, WarpTile<W> &wt, uint32_t m, int l
     if (x.count == 0u || x.count > a.urn_max) continue;
     const LevelInfo lv = level_info(a.P, x.pad_ & 0xFFu);
     uint32_t *row = wt.val + it * stride + (1u << tree_log2(lv.d));
-    const uint64_t picks = urn_picks(a, lv, wt.nbase[it], x.count, key, x.node_key);
+    const uint64_t picks = urn_picks(a, lv, x.node, wt.nbase[it], x.count, key, x.node_key);
     for (uint32_t b = 0; b < x.count; ++b) row[(uint32_t)(picks >> (8u * b)) & 0xFFu] += 1u;
     stat[kStatUrnItems] += 1;
   }

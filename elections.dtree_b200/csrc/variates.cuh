@@ -64,13 +64,12 @@ __device__ __forceinline__ float gamma_variate(float alpha, RngKey key, uint64_t
 
 // ---------------------------------------------------------------------------------------------
 // Stirling tail fc(k) = log(k!) - [ (k+1/2) log(k+1) - (k+1) + log(2 pi)/2 ]  (Hörmann 1993).
+__device__ const double kStirlingTail[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983,
+                                             0.02079067210376509, 0.0166446911898211, 0.0138761288230707,
+                                             0.0118967099458917, 0.0104112652619720, 0.00925546218271273,
+                                             0.00833056343336287};
 __device__ __forceinline__ double stirling_tail(double k) {
-  if (k <= 9.0) {
-    const double t[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509,
-                          0.0166446911898211, 0.0138761288230707, 0.0118967099458917, 0.0104112652619720,
-                          0.00925546218271273, 0.00833056343336287};
-    return t[(int)k];
-  }
+  if (k <= 9.0) return kStirlingTail[(int)k];
   double kp1sq = (k + 1.0) * (k + 1.0);
   return (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / (k + 1.0);
 }
