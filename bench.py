@@ -152,7 +152,7 @@ def run_reference(args, cfg, name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
@@ -161,6 +161,9 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--urn-max", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-mode", action="store_true", help="do not also time the other kernel")
+    ap.add_argument("--mode", type=int, default=-1, choices=[-1, 0, 1],
+                    help="1: deferred expansion kernel, 0: materialising kernel, -1: the library's choice")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -195,6 +198,7 @@ def main():
         t.tune(block_threads=args.block_threads, blocks_per_sm=args.blocks_per_sm)
     if args.urn_max >= 0:
         t.tune(urn_max=args.urn_max)
+    t.tune(mode=args.mode)
     L = N.lib()
     N.check(L.dtree_sync_device(t._h))
     seed = SEED.encode()
@@ -203,55 +207,65 @@ def main():
 
     total = torch.zeros(nc, dtype=torch.int64, device=dev)
 
-    def step(i):
-        # global election ids: step i covers [i*epg*world, (i+1)*epg*world); this rank's contiguous share
-        first = (i * world + rank) * epg
-        wins.zero_()
-        N.check(L.dtree_sample_posterior_device(t._h, first, epg, cfg["n_ballots"], 1, 0, seed, len(seed),
-                                                wins.data_ptr(), stream.cuda_stream))
-        if world > 1:
-            dist.all_reduce(wins, op=dist.ReduceOp.SUM)
-        total.add_(wins)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
-        step(i)
-    N.check(L.dtree_sample_posterior_finish(t._h, stream.cuda_stream))
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    kernel_ev = []
-    total.zero_()
-    ev[0].record(stream)
-    for i in range(args.steps):
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        first = ((args.warmup + i) * world + rank) * epg
-        wins.zero_()
-        k0.record(stream)
-        N.check(L.dtree_sample_posterior_device(t._h, first, epg, cfg["n_ballots"], 1, 0, seed, len(seed),
-                                                wins.data_ptr(), stream.cuda_stream))
-        k1.record(stream)
-        kernel_ev.append((k0, k1))
+    def measure(mode, n_el, steps, warmup, offset):
+        """K timed steps of n_el elections per GPU with the tree resident and the counts left on the device."""
+        t.tune(mode=mode)
+
+        def launch(i):
+            # global election ids: step i covers [i*n_el*world, (i+1)*n_el*world); this rank's contiguous share
+            first = offset + (i * world + rank) * n_el
+            wins.zero_()
+            N.check(L.dtree_sample_posterior_device(t._h, first, n_el, cfg["n_ballots"], 1, 0, seed, len(seed),
+                                                    wins.data_ptr(), stream.cuda_stream))
+
+        for i in range(warmup):
+            launch(i)
+            if world > 1:
+                dist.all_reduce(wins, op=dist.ReduceOp.SUM)
+        N.check(L.dtree_sample_posterior_finish(t._h, stream.cuda_stream))
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kernel_ev = []
+        total.zero_()
+        ev0.record(stream)
+        for i in range(steps):
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            launch(warmup + i)
+            k1.record(stream)
+            kernel_ev.append((k0, k1))
+            if world > 1:
+                dist.all_reduce(wins, op=dist.ReduceOp.SUM)
+            total.add_(wins)
+        ev1.record(stream)
+        barrier()
+        N.check(L.dtree_sample_posterior_finish(t._h, stream.cuda_stream))
+        st = t.last_stats()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(wins, op=dist.ReduceOp.SUM)
-        total.add_(wins)
-        ev[i + 1].record(stream)
-    barrier()
-    N.check(L.dtree_sample_posterior_finish(t._h, stream.cuda_stream))
-    stats = t.last_stats()
-    elapsed_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_ev]))
-    el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(el.item())
-    total_wins = int(total.sum().item())
-    assert total_wins == epg * world * args.steps, (total_wins, epg * world * args.steps)
-    value = epg * world * args.steps / (elapsed_ms / 1e3)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        assert int(total.sum().item()) == n_el * world * steps
+        return {"value": n_el * world * steps / (ms / 1e3), "elapsed_ms": ms, "steps": steps, "elections_per_gpu": n_el,
+                "kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in kernel_ev])), "stats": st,
+                "kernel": "deferred_kernel" if st["mode"] == 1 else "simulate_kernel"}
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    main = measure(args.mode, epg, args.steps, args.warmup, 0)
+    stats = main["stats"]
+    elapsed_ms, kernel_ms, value = main["elapsed_ms"], main["kernel_ms"], main["value"]
+    # the other kernel on the same inputs (fewer elections when it is the slower, materialising one)
+    other = None
+    if not args.single_mode:
+        om = 0 if stats["mode"] == 1 else 1
+        o_epg = max(296, epg // 8) if om == 0 else epg
+        other = measure(om, o_epg, max(2, min(args.steps, 3)), 3, 1 << 40)
+    t.tune(mode=args.mode)
 
     # ---- e2e: host buffers through the C ABI, mirror invalidated so that the tree upload is inside -------------
     e2e_steps = max(1, min(args.steps, 3))
@@ -314,27 +328,44 @@ def main():
                                             "binomial_attempts": stats["binomial_attempts"] / max(stats["elections"], 1),
                                             "items": stats["items"] / max(stats["elections"], 1),
                                             "urn_items": stats["urn_items"] / max(stats["elections"], 1)}}
+        if other is not None and other["kernel"] == "simulate_kernel":
+            denominators["kernel_counters"]["items_full"] = other["stats"]["items"] / max(other["stats"]["elections"], 1)
         threads = host_threads()
         n_cpu = cpu_sample_size(cfg, threads)
         _, secs = cpu_run(olib, cfg, prefs, offsets, n_cpu, threads, SEED)
         cpu_baseline = {"value": n_cpu / secs, "unit": "elections/s", "cores": threads, "kind": kind,
                         "sample": "%d elections of the same workload in %.1f s, %d threads (R_tree.cpp:213-242 pool)" % (n_cpu, secs, threads)}
-    achieved = b_alg * epg / (kernel_ms / 1e3) / 1e9
+    def roofline(m):
+        ach = b_alg * m["elections_per_gpu"] / (m["kernel_ms"] / 1e3) / 1e9
+        return {"kernel": m["kernel"], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_election": b_alg,
+                "kernel_ms_per_launch": m["kernel_ms"], "elections_per_launch": m["elections_per_gpu"]}
+
+    rl = roofline(main)
+    rl["denominators"] = denominators
+    if main["kernel"] == "deferred_kernel":
+        rl["note"] = ("algorithmic bytes are SURVEY 8(d)'s, i.e. what materialising every ballot moves; this kernel splits only "
+                      "the nodes IRV asks about (%.0f of the %.0f a full expansion visits) and writes no ballot list, so its "
+                      "DRAM traffic is far below them; see `materialised` for the kernel that does move them"
+                      % (stats["items"] / max(stats["elections"], 1), denominators.get("kernel_counters", {}).get("items_full", float("nan"))))
     line = {
         "metric": METRIC, "value": value, "unit": "elections/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 Gamma variates + f64 binomial rejection; u32 counts/tallies", "data": "synthetic",
         "config": {"workload": describe(name, cfg, epg), "global_elections_per_step": epg * world,
-                   "cache": "working set larger than L2: %.1f GB of per-election scratch streamed per step" % (stats["scratch_bytes"] / 1e9),
+                   "kernel": main["kernel"],
+                   "cache": "per-election scratch far larger than L2 (%.1f GB reserved); nothing is reused between elections"
+                            % (stats["scratch_bytes"] / 1e9),
                    "parallelism": "elections sharded over %d GPU(s), tree replicated, one all-reduce of %d win counts" % (world, nc),
                    "seed": SEED},
         "e2e": e2e, "gpu_launches": int(stats["launches"]) * args.steps,
-        "roofline": {"kernel": "simulate_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_election": b_alg, "kernel_ms_per_launch": kernel_ms,
-                     "denominators": denominators},
-        "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": rl, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
+    if other is not None:
+        key = "materialised" if other["kernel"] == "simulate_kernel" else "deferred"
+        line[key] = {"kernel": other["kernel"], "value": other["value"], "unit": "elections/s", "steps": other["steps"],
+                     "elections_per_gpu_per_step": other["elections_per_gpu"], "roofline": roofline(other),
+                     "note": "same inputs and seed; outcomes are bit-identical to the headline kernel's"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

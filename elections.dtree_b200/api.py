@@ -164,7 +164,7 @@ class dirichlet_tree:
         buf = (C.c_uint64 * 16)()
         N.check(self._L.dtree_last_stats(self._h, buf, 16))
         keys = ["launches", "elections", "entries", "items", "gammas", "binomial_attempts", "irv_rereads",
-                "scratch_bytes", "h2d_bytes", "d2h_bytes", "slots", "urn_items", "mode"]
+                "scratch_bytes", "h2d_bytes", "d2h_bytes", "slots", "urn_items", "mode", "arena_runs"]
         return {k: int(buf[i]) for i, k in enumerate(keys)}
 
     # ---- ballots ------------------------------------------------------------------------------------

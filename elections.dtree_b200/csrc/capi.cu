@@ -125,10 +125,21 @@ struct dtree {
   DevBuf<int> d_error;
   DevBuf<uint32_t> d_entry_count;
   DevBuf<uint8_t> d_orders;
+  // deferred kernel: worst-case overflow arenas, their locks, usage high-water marks [3] + arena runs [1]
+  DevBuf<uint8_t> d_arena;
+  DevBuf<unsigned int> d_locks, d_usage;
+  struct Sizing {
+    bool valid = false;
+    uint64_t version = 0;
+    uint32_t n_sample = 0, urn_max = 0, min_depth = 0, max_depth = 0;
+    double a0 = 0;
+    bool vd = false, use_obs = false;
+    uint32_t pool = 0, queue = 0, big = 0;
+  } sizing;
   // tuning
   int block_threads = 0, blocks_per_sm = 0;
   uint32_t urn_max = 8;
-  int mode = 1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel)
+  int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
   // callbacks, stats
   int (*should_abort)(void *) = nullptr;
   void *abort_user = nullptr;
@@ -197,6 +208,8 @@ struct Plan {
   int W, block, grid, blocks_per_sm;
   bool log_gamma;
   uint32_t cap_items, cap_entries, cap_queue = 0, cap_big = 0;
+  uint32_t n_arenas = 0, arena_items = 0, arena_queue = 0, arena_big = 0;
+  uint64_t arena_stride = 0, mem_budget = 0;
   uint64_t stride;        // scratch bytes per block (materialising kernel) or per warp (deferred kernel)
   uint64_t stride_block;  // scratch bytes per block
   bool deferred = false;
@@ -258,8 +271,11 @@ int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, P
   return DTREE_OK;
 }
 
-// Launch shape and scratch of deferred_kernel: one warp per election, three item arrays per warp
-// (parked nodes + two frontiers), each able to hold every distinct prefix an election can touch.
+// Launch shape and scratch of deferred_kernel: one warp per election. Each warp gets an arena sized
+// from measured usage (pl.cap_*); a few shared arenas hold the proven worst case (pl.arena_*): a sampled
+// ballot sits in at most one live node, and a node with only observed ballots is a tree node.
+constexpr uint32_t kMaxArenas = 8;
+
 int make_plan_deferred(dtree *t, uint32_t n_sample, uint32_t n_elections, Plan &pl) {
   const HostParams &P = t->tree.P;
   pl.W = 1;
@@ -270,24 +286,33 @@ int make_plan_deferred(dtree *t, uint32_t n_sample, uint32_t n_elections, Plan &
   if (occ <= 0) return fail(DTREE_ERR_CUDA, "deferred kernel cannot be resident (%s)", cudaGetErrorString(cudaGetLastError()));
   if (t->blocks_per_sm > 0) occ = std::min(occ, t->blocks_per_sm);
   pl.blocks_per_sm = occ;
-  const int wpb = pl.block / 32;
-  // A sampled ballot sits in at most one live node; a node with only observed ballots is a tree node.
   uint64_t worst = (uint64_t)n_sample + t->tree.n_nodes() + 64;
-  if (worst > 0x7FFFFFF0ull) return fail(DTREE_ERR_ARG, "n_ballots too large for the deferred kernel; use mode 0");
-  pl.cap_items = (uint32_t)worst;
-  pl.cap_entries = 0;
-  pl.cap_queue = (uint32_t)worst;
-  pl.cap_big = (uint32_t)((uint64_t)n_sample / (t->urn_max + 1) + 64);
-  pl.stride = (deferred_scratch_bytes(pl.cap_items, pl.cap_queue, pl.cap_big) + 255) & ~255ull;  // per warp
-  uint64_t grid = std::min<uint64_t>((uint64_t)occ * t->sm_count, ((uint64_t)n_elections + wpb - 1) / wpb);
+  if (worst > 0x7FFFFFF0ull) {
+    pl.n_arenas = 0;
+    return DTREE_OK;  // caller falls back to the materialising kernel
+  }
+  pl.arena_items = (uint32_t)worst;
+  pl.arena_queue = (uint32_t)worst;
+  pl.arena_big = (uint32_t)((uint64_t)n_sample / (t->urn_max + 1) + 64);
+  pl.arena_stride = (deferred_scratch_bytes(pl.arena_items, pl.arena_queue, pl.arena_big) + 255) & ~255ull;
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  uint64_t budget = (uint64_t)((double)(free_b + t->d_scratch.n) * 0.6);
-  uint64_t fit = budget / (pl.stride * wpb);
-  if (fit == 0) return fail(DTREE_ERR_CUDA, "not enough device memory for one block of deferred scratch");
-  pl.grid = (int)std::max<uint64_t>(1, std::min(grid, fit));
-  pl.stride_block = pl.stride * wpb;
+  const uint64_t avail = free_b + t->d_scratch.n + t->d_arena.n;
+  pl.n_arenas = (uint32_t)std::min<uint64_t>(kMaxArenas, (uint64_t)((double)avail * 0.25) / pl.arena_stride);
+  pl.cap_entries = 0;
+  pl.mem_budget = (uint64_t)((double)avail * 0.5);
+  (void)n_elections;
   return DTREE_OK;
+}
+
+// Sizes the per-warp arenas from pl.cap_* and fits the grid into the memory budget.
+void shape_deferred(dtree *t, uint32_t n_elections, Plan &pl) {
+  const int wpb = pl.block / 32;
+  pl.stride = (deferred_scratch_bytes(pl.cap_items, pl.cap_queue, pl.cap_big) + 255) & ~255ull;  // per warp
+  pl.stride_block = pl.stride * wpb;
+  uint64_t grid = std::min<uint64_t>((uint64_t)pl.blocks_per_sm * t->sm_count, ((uint64_t)n_elections + wpb - 1) / wpb);
+  uint64_t fit = std::max<uint64_t>(1, pl.mem_budget / pl.stride_block);
+  pl.grid = (int)std::max<uint64_t>(1, std::min(grid, fit));
 }
 
 void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
@@ -326,6 +351,21 @@ int check_sampling_args(dtree *t, uint32_t n_ballots, const char *seed, size_t s
   return DTREE_OK;
 }
 
+// Reads the deferred kernel's high-water marks and grows the cached sizing if an election came close.
+int absorb_usage(dtree *t) {
+  if (!t->d_usage.p) return DTREE_OK;
+  unsigned int u[4];
+  CUDA_TRY(cudaMemcpy(u, t->d_usage.p, sizeof u, cudaMemcpyDeviceToHost));
+  dtree::Sizing &z = t->sizing;
+  if (z.valid) {
+    z.pool = std::max(z.pool, u[0]);
+    z.queue = std::max(z.queue, u[1]);
+    z.big = std::max(z.big, u[2]);
+  }
+  t->stats[13] = u[3];
+  return DTREE_OK;
+}
+
 // Common body of the two sample_posterior entry points. d_wins must be device memory on t->device.
 int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots, uint32_t n_winners,
                   int replace, const char *seed, size_t seed_len, unsigned long long *d_wins, uint8_t *h_orders,
@@ -343,9 +383,21 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   const uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->tree.n_observed();
   Plan pl;
   pl.deferred = t->mode == 1;
-  rc = pl.deferred ? make_plan_deferred(t, n_sample, n_elections, pl) : make_plan(t, n_sample, n_elections, use_obs, pl);
-  if (rc) return rc;
-  CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));
+  if (t->mode < 0) {
+    // Tiny ballot spaces (a few dozen prefixes) are cheaper to enumerate than to park and re-visit.
+    double prefixes = 0;
+    for (uint32_t l = 0; l < nc; ++l) prefixes += falling_factorial(nc, l);
+    pl.deferred = prefixes > 256.0;
+  }
+  if (pl.deferred) {
+    rc = make_plan_deferred(t, n_sample, n_elections, pl);
+    if (rc) return rc;
+    if (pl.n_arenas == 0) pl.deferred = false;  // not even one worst-case arena fits: materialise instead
+  }
+  if (!pl.deferred) {
+    rc = make_plan(t, n_sample, n_elections, use_obs, pl);
+    if (rc) return rc;
+  }
   CUDA_TRY(t->d_counter.reserve(1));
   CUDA_TRY(t->d_error.reserve(1));
   CUDA_TRY(t->d_stats.reserve(kStatCount));
@@ -354,26 +406,100 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   if (h_orders) CUDA_TRY(t->d_orders.reserve((size_t)n_elections * nc));
 
   SimArgs a;
-  fill_args(t, pl, a);
-  a.obs_key = t->d_obs_key.p;
-  a.obs_cnt = t->d_obs_cnt.p;
-  a.obs_first = t->d_obs_first.p;
-  a.obs_tally0 = t->d_obs_tally0.p;
-  a.n_obs = use_obs ? t->n_obs_entries : 0;
-  a.use_obs = use_obs ? 1 : 0;
-  a.seed = hash_seed(seed, seed_len);
-  a.n_sample = n_sample;
-  a.n_winners = n_winners;
-  a.run_irv = 1;
-  a.win_counts = d_wins;
+  memset(&a, 0, sizeof a);
+  auto fill_job = [&](SimArgs &a) {
+    fill_args(t, pl, a);
+    a.obs_key = t->d_obs_key.p;
+    a.obs_cnt = t->d_obs_cnt.p;
+    a.obs_first = t->d_obs_first.p;
+    a.obs_tally0 = t->d_obs_tally0.p;
+    a.n_obs = use_obs ? t->n_obs_entries : 0;
+    a.use_obs = use_obs ? 1 : 0;
+    a.seed = hash_seed(seed, seed_len);
+    a.n_sample = n_sample;
+    a.n_winners = n_winners;
+    a.run_irv = 1;
+    a.win_counts = d_wins;
+  };
+
+  uint32_t pilot_done = 0;
+  uint64_t launches = 0;
+  if (pl.deferred) {
+    const HostParams &P = t->tree.P;
+    dtree::Sizing &z = t->sizing;
+    const bool hit = z.valid && z.version == t->tree.version() && z.n_sample == n_sample && z.urn_max == t->urn_max &&
+                     z.min_depth == P.min_depth && z.max_depth == P.max_depth && z.a0 == P.a0 && z.vd == P.vd &&
+                     z.use_obs == use_obs;
+    CUDA_TRY(t->d_arena.reserve(pl.arena_stride * pl.n_arenas));
+    if (t->d_locks.n < kMaxArenas) {
+      CUDA_TRY(t->d_locks.reserve(kMaxArenas));
+      CUDA_TRY(cudaMemsetAsync(t->d_locks.p, 0, kMaxArenas * sizeof(unsigned int), s));
+    }
+    CUDA_TRY(t->d_usage.reserve(4));
+    CUDA_TRY(cudaMemsetAsync(t->d_usage.p, 0, 4 * sizeof(unsigned int), s));
+    if (!hit) {
+      // Pilot: a few elections run directly in the worst-case arenas (they cannot overflow and their
+      // results count); their high-water marks size everybody else's arena.
+      Plan pp = pl;
+      pp.cap_items = pl.arena_items;
+      pp.cap_queue = pl.arena_queue;
+      pp.cap_big = pl.arena_big;
+      pp.stride = pl.arena_stride;
+      const int wpb = pp.block / 32;
+      pp.grid = (int)((pl.n_arenas + wpb - 1) / wpb);
+      pilot_done = std::min<uint32_t>(n_elections, 4 * pl.n_arenas);
+      SimArgs ap;
+      Plan saved = pl;
+      pl = pp;
+      fill_job(ap);
+      pl = saved;
+      ap.scratch = t->d_arena.p;
+      ap.scratch_stride = pl.arena_stride;
+      ap.max_warps = pl.n_arenas;
+      ap.n_arenas = 0;
+      ap.usage = t->d_usage.p;
+      ap.arena_runs = t->d_usage.p + 3;
+      ap.first_election = first_election;
+      ap.n_elections = pilot_done;
+      ap.elim_orders = h_orders ? t->d_orders.p : nullptr;
+      CUDA_TRY(cudaMemsetAsync(t->d_counter.p, 0, sizeof(unsigned int), s));
+      CUDA_TRY(launch(pp, ap, s));
+      ++launches;
+      CUDA_TRY(cudaStreamSynchronize(s));
+      unsigned int u[4];
+      CUDA_TRY(cudaMemcpy(u, t->d_usage.p, sizeof u, cudaMemcpyDeviceToHost));
+      z.valid = true;
+      z.version = t->tree.version();
+      z.n_sample = n_sample; z.urn_max = t->urn_max; z.min_depth = P.min_depth; z.max_depth = P.max_depth;
+      z.a0 = P.a0; z.vd = P.vd; z.use_obs = use_obs;
+      z.pool = u[0]; z.queue = u[1]; z.big = u[2];
+    }
+    pl.cap_items = (uint32_t)std::min<uint64_t>(pl.arena_items, 2ull * z.pool + 1024);
+    pl.cap_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 2ull * z.queue + 1024);
+    pl.cap_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 2ull * z.big + 256);
+    shape_deferred(t, n_elections - pilot_done, pl);
+  }
+  CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));
+  fill_job(a);
+  if (pl.deferred) {
+    a.arena_scratch = t->d_arena.p;
+    a.arena_stride = pl.arena_stride;
+    a.n_arenas = pl.n_arenas;
+    a.arena_cap_items = pl.arena_items;
+    a.arena_cap_queue = pl.arena_queue;
+    a.arena_cap_big = pl.arena_big;
+    a.arena_locks = t->d_locks.p;
+    a.usage = t->d_usage.p;
+    a.arena_runs = t->d_usage.p + 3;
+    a.max_warps = 0xFFFFFFFFu;
+  }
 
   // One launch per wave. Without an abort callback the whole range is one wave.
   uint32_t wave = n_elections;
   if (t->should_abort) wave = (uint32_t)std::min<uint64_t>(n_elections, (uint64_t)pl.grid * (pl.deferred ? 4096 : 64));
-  uint64_t launches = 0;
-  for (uint32_t done = 0; done < n_elections; done += wave) {
+  for (uint32_t done = pilot_done; done < n_elections; done += wave) {
     uint32_t n = std::min(wave, n_elections - done);
-    if (t->should_abort && done > 0) {
+    if (t->should_abort && done > pilot_done) {
       CUDA_TRY(cudaStreamSynchronize(s));
       if (t->should_abort(t->abort_user)) return fail(DTREE_ERR_ABORTED, "aborted by the host");
     }
@@ -402,6 +528,10 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   t->stats[6] = st[kStatRereads];
   t->stats[10] = st[kStatSlots];
   t->stats[11] = st[kStatUrnItems];
+  if (pl.deferred) {
+    rc = absorb_usage(t);
+    if (rc) return rc;
+  }
   if (h_orders) {
     CUDA_TRY(cudaMemcpy(h_orders, t->d_orders.p, (size_t)n_elections * nc, cudaMemcpyDeviceToHost));
     t->stats[9] += (uint64_t)n_elections * nc;
@@ -526,6 +656,7 @@ int dtree_destroy(dtree_t *t) {
     t->d_slot_child.release(); t->d_slot_cand.release(); t->d_obs_first.release(); t->d_obs_key.release();
     t->d_scratch.release(); t->d_wins.release(); t->d_stats.release(); t->d_counter.release(); t->d_error.release();
     t->d_entry_count.release(); t->d_orders.release();
+    t->d_arena.release(); t->d_locks.release(); t->d_usage.release();
   }
   delete t;
   return DTREE_OK;
@@ -710,6 +841,7 @@ int dtree_sample_posterior_finish(dtree_t *t, void *stream) {
   t->stats[6] = st[kStatRereads];
   t->stats[10] = st[kStatSlots];
   t->stats[11] = st[kStatUrnItems];
+  if (t->stats[12] == 1) return absorb_usage(t);
   return DTREE_OK;
 }
 
@@ -848,7 +980,7 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   if (!strcmp(key, "block_threads")) t->block_threads = (int)value;
   else if (!strcmp(key, "blocks_per_sm")) t->blocks_per_sm = (int)value;
   else if (!strcmp(key, "mode")) {
-    if (value != 0 && value != 1) return fail(DTREE_ERR_ARG, "mode must be 0 (materialise) or 1 (deferred)");
+    if (value < -1 || value > 1) return fail(DTREE_ERR_ARG, "mode must be -1 (auto), 0 (materialise) or 1 (deferred)");
     t->mode = (int)value;
   } else if (!strcmp(key, "urn_max")) {
     if (value < 0 || value > 8) return fail(DTREE_ERR_ARG, "urn_max must be in [0, 8]");

@@ -32,8 +32,14 @@ namespace dtb {
 
 typedef Item<1> DItem;  // prefix unused; pad_ = depth
 
+// Scratch capacities of the arena an election runs in (items).
+struct DeferredCaps {
+  uint32_t pool, queue, big;
+};
+
 struct DeferredWarp {
   uint32_t tally[kMaxCandidates];
+  uint32_t q_head;    // mirror of the drain loop's head, for the queue-occupancy check
   uint32_t n_pool;    // high-water mark of the parked-node pool
   int32_t n_free;     // free-list depth (may dip below 0 while lanes race for the last free slots)
   uint32_t q_tail;    // small-count work queue (circular, monotone counters; q_head is a register)
@@ -69,14 +75,15 @@ struct DeferredScratch {
 
 // Puts a node that must be split in the current round on the right transient list.
 __device__ __forceinline__ void enqueue_node(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
-                                             const DItem &ch, int big_sel) {
+                                             const DeferredCaps &cp, const DItem &ch, int big_sel) {
   if (ch.count > a.urn_max) {
     const uint32_t q = coalesced_reserve(&ws.big_tail);
-    if (q < a.cap_big) sc.big[big_sel][q] = ch;
+    if (q < cp.big) sc.big[big_sel][q] = ch;
     else ws.overflow = 1;
   } else {
     const uint32_t q = coalesced_reserve(&ws.q_tail);
-    sc.queue[q % a.cap_queue] = ch;
+    if (q - ws.q_head < cp.queue) sc.queue[q % cp.queue] = ch;  // q_head only grows: the test is conservative
+    else ws.overflow = 1;
   }
 }
 
@@ -84,7 +91,7 @@ __device__ __forceinline__ void enqueue_node(const SimArgs &a, DeferredWarp &ws,
 // lanes (divergent code). `tot` ballots now have `cand` as their next preference; `cs` of them are
 // sampled ballots that continue below the child, `child` is the child's CSR node (-1: none).
 __device__ __forceinline__ void route_child(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
-                                            const DItem &x, uint32_t depth, uint32_t eliminated, uint32_t cand,
+                                            const DeferredCaps &cp, const DItem &x, uint32_t depth, uint32_t eliminated, uint32_t cand,
                                             uint32_t tot, uint32_t cs, int32_t child, bool has_obs, int big_sel) {
   const bool standing = !(eliminated >> cand & 1u);
   if (standing) atomicAdd(&ws.tally[cand], tot);
@@ -98,7 +105,7 @@ __device__ __forceinline__ void route_child(const SimArgs &a, DeferredWarp &ws, 
   ch.used = x.used | (1u << cand);
   ch.pad_ = depth + 1u;
   if (!standing) {  // its candidate is already out: split it in this round as well
-    enqueue_node(a, ws, sc, ch, big_sel);
+    enqueue_node(a, ws, sc, cp, ch, big_sel);
     return;
   }
   // park it under `cand`: reuse a freed pool slot if there is one, else grow the pool
@@ -115,7 +122,7 @@ __device__ __forceinline__ void route_child(const SimArgs &a, DeferredWarp &ws, 
   uint32_t j;
   if (rank < from_free) j = sc.free_list[old_free - 1 - rank];
   else j = grow_base + (uint32_t)(rank - from_free);
-  if (j >= a.cap_items) {
+  if (j >= cp.pool) {
     ws.overflow = 1;
     return;
   }
@@ -125,7 +132,7 @@ __device__ __forceinline__ void route_child(const SimArgs &a, DeferredWarp &ws, 
 
 // One lane splits one node with a small sampled count (0..urn_max) and routes its children.
 __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
-                                                 const DItem &x, uint32_t eliminated, const RngKey key, int big_sel,
+                                                 const DeferredCaps &cp, const DItem &x, uint32_t eliminated, const RngKey key, int big_sel,
                                                  uint32_t *stat) {
   const uint32_t nc = a.P.nc;
   const uint32_t depth = x.pad_ & 0xFFu;
@@ -147,7 +154,7 @@ __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp 
       const uint32_t c = (uint32_t)(c4[slot >> 4] >> (4u * (slot & 15u))) & 15u;
       const uint32_t obs = a.T.slot_count[nb + slot];
       if (c + obs == 0u) continue;
-      route_child(a, ws, sc, x, depth, eliminated, a.T.slot_cand[nb + slot], c + obs, lv.leaf_children ? 0u : c,
+      route_child(a, ws, sc, cp, x, depth, eliminated, a.T.slot_cand[nb + slot], c + obs, lv.leaf_children ? 0u : c,
                   a.T.slot_child[nb + slot], obs > 0u, big_sel);
     }
   } else {
@@ -165,7 +172,7 @@ __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp 
       if (slot == lv.K) continue;  // the ballots stop here: exhausted
       const uint32_t cand = nb != 0xFFFFFFFFu ? (uint32_t)a.T.slot_cand[nb + slot] : nth_unused(x.used, nc, slot);
       const int32_t child = nb != 0xFFFFFFFFu ? a.T.slot_child[nb + slot] : -1;
-      route_child(a, ws, sc, x, depth, eliminated, cand, c, lv.leaf_children ? 0u : c, child, false, big_sel);
+      route_child(a, ws, sc, cp, x, depth, eliminated, cand, c, lv.leaf_children ? 0u : c, child, false, big_sel);
     }
   }
 }
@@ -173,7 +180,7 @@ __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp 
 // The warp splits a list of nodes with big sampled counts through the shared-memory tile.
 template <bool LOG>
 __device__ void split_big_nodes(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
-                                const DItem *list, uint32_t n_list, uint32_t eliminated, int log_dp_max,
+                                const DeferredCaps &cp, const DItem *list, uint32_t n_list, uint32_t eliminated, int log_dp_max,
                                 const RngKey key, int big_sel, uint32_t *stat) {
   const int lane = threadIdx.x & 31;
   const uint32_t nc = a.P.nc;
@@ -208,7 +215,7 @@ __device__ void split_big_nodes(const SimArgs &a, WarpTile<1> &wt, DeferredWarp 
         cand = nth_unused(x.used, nc, slot);
       }
       if (c + obs == 0u) continue;
-      route_child(a, ws, sc, x, depth, eliminated, cand, c + obs, lv.leaf_children ? 0u : c, child, obs > 0u, big_sel);
+      route_child(a, ws, sc, cp, x, depth, eliminated, cand, c + obs, lv.leaf_children ? 0u : c, child, obs > 0u, big_sel);
     }
     __syncwarp();
   }
@@ -217,8 +224,8 @@ __device__ void split_big_nodes(const SimArgs &a, WarpTile<1> &wt, DeferredWarp 
 // Splits everything that is queued, and whatever that enqueues, until nothing is left.
 template <bool LOG>
 __device__ void deferred_drain(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
-                               uint32_t &q_head, uint32_t eliminated, int log_dp_max, const RngKey key,
-                               uint32_t *stat) {
+                               const DeferredCaps &cp, uint32_t &q_head, uint32_t &hw_queue, uint32_t &hw_big,
+                               uint32_t eliminated, int log_dp_max, const RngKey key, uint32_t *stat) {
   const int lane = threadIdx.x & 31;
   int sel = 0;  // big[sel] is being filled
   for (;;) {
@@ -226,24 +233,123 @@ __device__ void deferred_drain(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &
     for (;;) {
       __syncwarp();
       const uint32_t tail = ws.q_tail;
-      if (q_head >= tail) break;
+      if (q_head >= tail || ws.overflow) break;
+      hw_queue = max(hw_queue, tail - q_head);
       const uint32_t i = q_head + lane;
+      DItem x;
+      if (i < tail) x = sc.queue[i % cp.queue];
       q_head = min(q_head + 32u, tail);
-      if (i < tail) {
-        const DItem x = sc.queue[i % a.cap_queue];
-        split_small_node(a, ws, sc, x, eliminated, key, sel, stat);
-      }
+      __syncwarp();  // the batch has been read: its queue slots may be reused from here on
+      if (lane == 0) ws.q_head = q_head;
+      __syncwarp();
+      if (i < tail) split_small_node(a, ws, sc, cp, x, eliminated, key, sel, stat);
     }
     __syncwarp();
-    const uint32_t n_big = min(ws.big_tail, a.cap_big);
-    if (n_big == 0) break;
+    const uint32_t n_big = min(ws.big_tail, cp.big);
+    if (n_big == 0 || ws.overflow) break;
+    hw_big = max(hw_big, n_big);
     __syncwarp();
     if (lane == 0) ws.big_tail = 0;
     __syncwarp();
-    split_big_nodes<LOG>(a, wt, ws, sc, sc.big[sel], n_big, eliminated, log_dp_max, key, sel ^ 1, stat);
+    split_big_nodes<LOG>(a, wt, ws, sc, cp, sc.big[sel], n_big, eliminated, log_dp_max, key, sel ^ 1, stat);
     sel ^= 1;
   }
   __syncwarp();
+}
+
+// One election in the arena (sc, cp). Returns false if the arena was too small (nothing is recorded then).
+// On success *eliminated_out / *order_out / *ties_out describe the outcome (lane r holds round r's loser).
+template <bool LOG>
+__device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
+                                  const DeferredCaps &cp, const RngKey key, uint32_t n_rounds, int log_dp_max,
+                                  uint32_t *usage, uint32_t &eliminated_out, uint32_t &order_out, uint32_t &ties_out,
+                                  uint32_t *stat) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nc = a.P.nc;
+  ws.tally[lane] = 0;
+  if (lane == 0) {
+    DItem root;
+    root.prefix.w[0] = 0;
+    root.node_key = kRootNodeKey;
+    root.count = a.n_sample;
+    root.node = 0;
+    root.used = 0;
+    root.pad_ = 0;
+    ws.n_pool = 0;
+    ws.n_free = 0;
+    ws.overflow = 0;
+    ws.q_tail = 0;
+    ws.q_head = 0;
+    ws.big_tail = 0;
+    if (a.n_sample > a.urn_max) {
+      sc.big[0][0] = root;
+      ws.big_tail = 1;
+    } else {
+      sc.queue[0] = root;
+      ws.q_tail = 1;
+    }
+  }
+  __syncwarp();
+  uint32_t eliminated = 0, tie_rounds = 0, my_order = 0xFFu, q_head = 0, hw_queue = 0, hw_big = 0;
+  deferred_drain<LOG>(a, wt, ws, sc, cp, q_head, hw_queue, hw_big, eliminated, log_dp_max, key, stat);
+
+  for (uint32_t round = 0; round < n_rounds && !ws.overflow; ++round) {
+    // candidates with the minimal tally among those standing (irv_ballot.cpp:88-98), one lane each
+    const bool standing = lane < (int)nc && !(eliminated >> lane & 1u);
+    const uint32_t t = standing ? ws.tally[lane] : 0xFFFFFFFFu;
+    const uint32_t mn = __reduce_min_sync(0xffffffffu, t);
+    uint32_t tied = __ballot_sync(0xffffffffu, standing && t == mn);
+    const uint32_t ntied = (uint32_t)__popc(tied);
+    if (ntied > 1u) {  // uniform among the tied, ascending index (irv_ballot.cpp:100-102)
+      U4 r = node_random(key, 0ull, kStreamTie, round);
+      const uint32_t pick = uniform_below(r.x, ntied);
+      for (uint32_t k = 0; k < pick; ++k) tied &= tied - 1u;
+      tie_rounds += 1;
+    }
+    const uint32_t chosen = (uint32_t)__ffs(tied) - 1u;
+    if (lane == (int)round) my_order = chosen;
+    eliminated |= 1u << chosen;
+    if (mn == 0u) continue;  // nobody counts for this candidate: nothing is parked under it
+    // queue the nodes parked under the eliminated candidate: scan the holder bytes 16 per lane
+    if (lane == 0 && ws.n_free < 0) ws.n_free = 0;
+    __syncwarp();
+    const uint32_t np = min(ws.n_pool, cp.pool);
+    const uint32_t n_vec = (np + 15u) / 16u;
+    const uint32_t pattern = chosen * 0x01010101u;
+    for (uint32_t vbase = 0; vbase < n_vec; vbase += 32) {
+      const uint32_t v = vbase + lane;
+      uint32_t hits = 0;
+      if (v < n_vec) {
+        const uint4 h = reinterpret_cast<const uint4 *>(sc.holder)[v];
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t eq = __vcmpeq4(hw[q], pattern);
+          hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * q);
+        }
+      }
+      while (hits) {
+        const uint32_t j = v * 16u + (uint32_t)__ffs(hits) - 1u;
+        hits &= hits - 1u;
+        if (j >= np) break;
+        sc.holder[j] = 0xFF;
+        const DItem x = sc.pool[j];
+        enqueue_node(a, ws, sc, cp, x, 0);
+        const uint32_t f = coalesced_reserve(reinterpret_cast<uint32_t *>(&ws.n_free));
+        sc.free_list[f] = j;
+      }
+    }
+    __syncwarp();
+    deferred_drain<LOG>(a, wt, ws, sc, cp, q_head, hw_queue, hw_big, eliminated, log_dp_max, key, stat);
+  }
+  __syncwarp();
+  usage[0] = max(usage[0], min(ws.n_pool, 0x7FFFFFFFu));
+  usage[1] = max(usage[1], hw_queue);
+  usage[2] = max(usage[2], hw_big);
+  eliminated_out = eliminated;
+  order_out = my_order;
+  ties_out = tie_rounds;
+  return ws.overflow == 0;
 }
 
 template <int BLOCK, bool LOG>
@@ -252,14 +358,19 @@ __global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__
   __shared__ DeferredWarp wstate[BLOCK / 32];
   __shared__ uint32_t s_wins[kMaxCandidates];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t nc = a.P.nc, cap = a.cap_items;
+  const uint32_t nc = a.P.nc;
   const uint32_t cand_mask = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u);
   WarpTile<1> &wt = tiles[warp];
   DeferredWarp &ws = wstate[warp];
+  const uint32_t gwarp = blockIdx.x * (BLOCK / 32) + warp;
+  // Each warp owns a right-sized arena; elections that outgrow it are re-run in one of a few
+  // worst-case arenas shared by the whole grid (try-lock; holders never wait, so no deadlock).
+  DeferredCaps cp{a.cap_items, a.cap_queue, a.cap_big};
   DeferredScratch sc;
-  sc.bind(a.scratch + ((uint64_t)blockIdx.x * (BLOCK / 32) + warp) * a.scratch_stride, cap, a.cap_queue, a.cap_big);
+  sc.bind(a.scratch + (uint64_t)gwarp * a.scratch_stride, cp.pool, cp.queue, cp.big);
+  const DeferredCaps cp_max{a.arena_cap_items, a.arena_cap_queue, a.arena_cap_big};
   const int log_dp_max = tree_log2(level_info(a.P, 0).d);
-  uint32_t stat[kStatCount];
+  uint32_t stat[kStatCount], usage[3] = {0u, 0u, 0u};
 #pragma unroll
   for (int i = 0; i < kStatCount; ++i) stat[i] = 0;
   if (tid < (int)kMaxCandidates) s_wins[tid] = 0;
@@ -267,90 +378,41 @@ __global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__
   const uint32_t n_rounds = a.elim_orders ? nc - 1 : nc - a.n_winners;
 
   for (;;) {
+    if (gwarp >= a.max_warps) break;
     uint32_t e = 0;
     if (lane == 0) e = atomicAdd(a.work_counter, 1u);
     e = __shfl_sync(0xffffffffu, e, 0);
     if (e >= a.n_elections) break;
     const RngKey key = election_key(a.seed, a.first_election + e);
-
-    ws.tally[lane] = 0;
-    if (lane == 0) {
-      DItem root;
-      root.prefix.w[0] = 0;
-      root.node_key = kRootNodeKey;
-      root.count = a.n_sample;
-      root.node = 0;
-      root.used = 0;
-      root.pad_ = 0;
-      ws.n_pool = 0;
-      ws.n_free = 0;
-      ws.overflow = 0;
-      ws.q_tail = 0;
-      ws.big_tail = 0;
-      if (a.n_sample > a.urn_max) {
-        sc.big[0][0] = root;
-        ws.big_tail = 1;
+    uint32_t eliminated = 0, my_order = 0xFFu, tie_rounds = 0;
+    bool ok = deferred_election<LOG>(a, wt, ws, sc, cp, key, n_rounds, log_dp_max, usage, eliminated, my_order,
+                                     tie_rounds, stat);
+    if (!ok) {
+      if (a.n_arenas == 0u) {
+        if (lane == 0) *a.error_flag = 2;
       } else {
-        sc.queue[0] = root;
-        ws.q_tail = 1;
-      }
-    }
-    __syncwarp();
-    uint32_t eliminated = 0, tie_rounds = 0, my_order = 0xFFu, q_head = 0;
-    deferred_drain<LOG>(a, wt, ws, sc, q_head, eliminated, log_dp_max, key, stat);
-
-    for (uint32_t round = 0; round < n_rounds; ++round) {
-      // candidates with the minimal tally among those standing (irv_ballot.cpp:88-98), one lane each
-      const bool standing = lane < (int)nc && !(eliminated >> lane & 1u);
-      const uint32_t t = standing ? ws.tally[lane] : 0xFFFFFFFFu;
-      const uint32_t mn = __reduce_min_sync(0xffffffffu, t);
-      uint32_t tied = __ballot_sync(0xffffffffu, standing && t == mn);
-      const uint32_t ntied = (uint32_t)__popc(tied);
-      if (ntied > 1u) {  // uniform among the tied, ascending index (irv_ballot.cpp:100-102)
-        U4 r = node_random(key, 0ull, kStreamTie, round);
-        const uint32_t pick = uniform_below(r.x, ntied);
-        for (uint32_t k = 0; k < pick; ++k) tied &= tied - 1u;
-        tie_rounds += 1;
-      }
-      const uint32_t chosen = (uint32_t)__ffs(tied) - 1u;
-      if (lane == (int)round) my_order = chosen;
-      eliminated |= 1u << chosen;
-      if (mn == 0u) continue;  // nobody counts for this candidate: nothing is parked under it
-      // queue the nodes parked under the eliminated candidate: scan the holder bytes 16 per lane
-      if (lane == 0 && ws.n_free < 0) ws.n_free = 0;
-      __syncwarp();
-      const uint32_t np = min(ws.n_pool, cap);
-      const uint32_t n_vec = (np + 15u) / 16u;
-      const uint32_t pattern = chosen * 0x01010101u;
-      for (uint32_t vbase = 0; vbase < n_vec; vbase += 32) {
-        const uint32_t v = vbase + lane;
-        uint32_t hits = 0;
-        if (v < n_vec) {
-          const uint4 h = reinterpret_cast<const uint4 *>(sc.holder)[v];
-          const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t eq = __vcmpeq4(hw[q], pattern);
-            hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * q);
+        uint32_t slot = 0;
+        if (lane == 0) {
+          slot = gwarp % a.n_arenas;
+          while (atomicCAS(&a.arena_locks[slot], 0u, 1u) != 0u) {
+            slot = (slot + 1u) % a.n_arenas;
+            __nanosleep(200);
           }
+          __threadfence();
+          atomicAdd(a.arena_runs, 1u);
         }
-        while (hits) {
-          const uint32_t j = v * 16u + (uint32_t)__ffs(hits) - 1u;
-          hits &= hits - 1u;
-          if (j >= np) break;
-          sc.holder[j] = 0xFF;
-          const DItem x = sc.pool[j];
-          enqueue_node(a, ws, sc, x, 0);
-          const uint32_t f = coalesced_reserve(reinterpret_cast<uint32_t *>(&ws.n_free));
-          sc.free_list[f] = j;
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        DeferredScratch big_sc;
+        big_sc.bind(a.arena_scratch + (uint64_t)slot * a.arena_stride, cp_max.pool, cp_max.queue, cp_max.big);
+        ok = deferred_election<LOG>(a, wt, ws, big_sc, cp_max, key, n_rounds, log_dp_max, usage, eliminated, my_order,
+                                    tie_rounds, stat);
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          atomicExch(&a.arena_locks[slot], 0u);
+          if (!ok) *a.error_flag = 2;
         }
       }
-      __syncwarp();
-      deferred_drain<LOG>(a, wt, ws, sc, q_head, eliminated, log_dp_max, key, stat);
-    }
-
-    if (ws.overflow) {
-      if (lane == 0) *a.error_flag = 2;
     }
     const uint32_t standing_mask = ~eliminated & cand_mask;
     if (a.elim_orders) {
@@ -368,6 +430,11 @@ __global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__
   }
   __syncthreads();
   if (tid < (int)nc && s_wins[tid]) atomicAdd(&a.win_counts[tid], (unsigned long long)s_wins[tid]);
+  if (a.usage && lane == 0) {
+    atomicMax(&a.usage[0], usage[0]);
+    atomicMax(&a.usage[1], usage[1]);
+    atomicMax(&a.usage[2], usage[2]);
+  }
   if (a.stats) {
 #pragma unroll
     for (int i = 0; i < kStatCount; ++i) {

@@ -52,6 +52,14 @@ struct SimArgs {
   uint32_t cap_items;         // frontier capacity (items) per buffer
   uint32_t cap_entries;
   uint32_t cap_queue, cap_big; // deferred kernel: circular work queue / big-count lists (items)
+  // deferred kernel: a few worst-case arenas for the elections that outgrow their warp's scratch
+  uint8_t *arena_scratch;
+  uint64_t arena_stride;
+  uint32_t n_arenas, arena_cap_items, arena_cap_queue, arena_cap_big;
+  unsigned int *arena_locks;   // [n_arenas], 0 = free
+  unsigned int *arena_runs;    // number of elections re-run in an arena
+  uint32_t *usage;             // [3] high-water marks: parked pool, work queue, big list
+  uint32_t max_warps;          // warps with a larger grid-wide index stay idle (pilot launches)
   // outputs
   unsigned long long *win_counts;  // [nc], added to
   uint8_t *elim_orders;            // NULL or [n_elections * nc]

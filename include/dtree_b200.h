@@ -162,9 +162,10 @@ void dtree_ballots_free(dtree_ballots_t *b);
 int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user);
 
 /* ---- tuning / introspection (not part of the reference interface) ----------------------------
- * key: "mode" — how dtree_sample_posterior* simulates an election: 1 (default) expands a tree node only
- *        when IRV needs to look below it; 0 materialises every sampled ballot first, as the reference does
- *        (dirichlet_tree.h:216-235 then irv_ballot.cpp:42-138). Both give bit-identical outcomes;
+ * key: "mode" — how dtree_sample_posterior* simulates an election: 1 expands a tree node only when IRV
+ *        needs to look below it; 0 materialises every sampled ballot first, as the reference does
+ *        (dirichlet_tree.h:216-235 then irv_ballot.cpp:42-138); -1 (default) picks 0 for ballot spaces of
+ *        at most 256 prefixes and 1 otherwise. Both give bit-identical outcomes;
  *      "block_threads" (0 = auto), "blocks_per_sm" (0 = auto), "urn_max" (largest count split by the
  *        Polya-urn shortcut instead of Gamma variates, <= 8).
  * Returns DTREE_ERR_ARG for an unknown key. */
@@ -173,7 +174,7 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value);
  *  [0] kernel launches, [1] elections simulated, [2] sampled entries written, [3] frontier items
  *  processed, [4] Gamma variates drawn, [5] binomial variates drawn, [6] IRV entry re-reads,
  *  [7] device bytes of scratch, [8] H2D bytes, [9] D2H bytes, [10] outcome slots read,
- *  [11] nodes split by the urn shortcut, [12] mode used. */
+ *  [11] nodes split by the urn shortcut, [12] mode used, [13] elections re-run in a worst-case arena. */
 int dtree_last_stats(const dtree_t *t, uint64_t *out, uint32_t cap);
 
 #ifdef __cplusplus
