@@ -359,6 +359,7 @@ def main():
                    "parallelism": "elections sharded over %d GPU(s), tree replicated, one all-reduce of %d win counts" % (world, nc),
                    "seed": SEED},
         "e2e": e2e, "gpu_launches": int(stats["launches"]) * args.steps,
+        "arena_reruns_last_step": int(stats.get("arena_runs", 0)),
         "roofline": rl, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
     if other is not None:

@@ -474,9 +474,9 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
       z.a0 = P.a0; z.vd = P.vd; z.use_obs = use_obs;
       z.pool = u[0]; z.queue = u[1]; z.big = u[2];
     }
-    pl.cap_items = (uint32_t)std::min<uint64_t>(pl.arena_items, 2ull * z.pool + 1024);
-    pl.cap_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 2ull * z.queue + 1024);
-    pl.cap_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 2ull * z.big + 256);
+    pl.cap_items = (uint32_t)std::min<uint64_t>(pl.arena_items, 4ull * z.pool + 4096);
+    pl.cap_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 4ull * z.queue + 4096);
+    pl.cap_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 4ull * z.big + 1024);
     shape_deferred(t, n_elections - pilot_done, pl);
   }
   CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));

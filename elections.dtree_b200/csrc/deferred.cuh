@@ -353,7 +353,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
 }
 
 template <int BLOCK, bool LOG>
-__global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__ SimArgs a) {
+__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) deferred_kernel(const __grid_constant__ SimArgs a) {
   __shared__ WarpTile<1> tiles[BLOCK / 32];
   __shared__ DeferredWarp wstate[BLOCK / 32];
   __shared__ uint32_t s_wins[kMaxCandidates];
@@ -385,13 +385,14 @@ __global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__
     if (e >= a.n_elections) break;
     const RngKey key = election_key(a.seed, a.first_election + e);
     uint32_t eliminated = 0, my_order = 0xFFu, tie_rounds = 0;
-    bool ok = deferred_election<LOG>(a, wt, ws, sc, cp, key, n_rounds, log_dp_max, usage, eliminated, my_order,
-                                     tie_rounds, stat);
-    if (!ok) {
-      if (a.n_arenas == 0u) {
-        if (lane == 0) *a.error_flag = 2;
-      } else {
-        uint32_t slot = 0;
+    // First in the warp's own arena; if that proves too small, once more in a worst-case arena.
+    bool ok = false;
+    for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
+      DeferredScratch cur_sc = sc;
+      DeferredCaps cur_cp = cp;
+      uint32_t slot = 0;
+      if (attempt == 1) {
+        if (a.n_arenas == 0u) break;
         if (lane == 0) {
           slot = gwarp % a.n_arenas;
           while (atomicCAS(&a.arena_locks[slot], 0u, 1u) != 0u) {
@@ -402,18 +403,18 @@ __global__ void __launch_bounds__(BLOCK) deferred_kernel(const __grid_constant__
           atomicAdd(a.arena_runs, 1u);
         }
         slot = __shfl_sync(0xffffffffu, slot, 0);
-        DeferredScratch big_sc;
-        big_sc.bind(a.arena_scratch + (uint64_t)slot * a.arena_stride, cp_max.pool, cp_max.queue, cp_max.big);
-        ok = deferred_election<LOG>(a, wt, ws, big_sc, cp_max, key, n_rounds, log_dp_max, usage, eliminated, my_order,
-                                    tie_rounds, stat);
-        __syncwarp();
-        if (lane == 0) {
-          __threadfence();
-          atomicExch(&a.arena_locks[slot], 0u);
-          if (!ok) *a.error_flag = 2;
-        }
+        cur_cp = cp_max;
+        cur_sc.bind(a.arena_scratch + (uint64_t)slot * a.arena_stride, cp_max.pool, cp_max.queue, cp_max.big);
+      }
+      ok = deferred_election<LOG>(a, wt, ws, cur_sc, cur_cp, key, n_rounds, log_dp_max, usage, eliminated, my_order,
+                                  tie_rounds, stat);
+      __syncwarp();
+      if (attempt == 1 && lane == 0) {
+        __threadfence();
+        atomicExch(&a.arena_locks[slot], 0u);
       }
     }
+    if (!ok && lane == 0) *a.error_flag = 2;
     const uint32_t standing_mask = ~eliminated & cand_mask;
     if (a.elim_orders) {
       uint8_t *o = a.elim_orders + (uint64_t)e * nc;

@@ -75,23 +75,23 @@ __device__ __forceinline__ double stirling_tail(double k) {
 }
 
 // Binomial(n, ps) for ps <= 1/2, exact.
-//  * n ps < 10: sequential inversion (BINV, Kachitvichyanukul & Schmeiser 1988) on one uniform;
+//  * n ps < 30: sequential inversion (BINV, Kachitvichyanukul & Schmeiser 1988) on one uniform;
 //  * otherwise: BTRS, transformed rejection with squeeze (Hörmann 1993), in double because the
 //    candidate k = floor((2a/us + b)u + c) must be an exact integer up to n < 2^32.
 __device__ __forceinline__ uint32_t binomial_small_p(uint32_t n, float ps, RngKey key, uint64_t node_key,
                                                      uint32_t slot, uint32_t &attempts) {
   if (n == 0u || !(ps > 0.0f)) return 0u;
   const float nf = (float)n;
-  if (__fmul_rn(nf, ps) < 10.0f) {
+  if (__fmul_rn(nf, ps) < 30.0f) {
     U4 r = node_random(key, node_key, kStreamBinomial + slot, 0u);
     ++attempts;
     float qs = __fadd_rn(1.0f, -ps);
     float s = __fdividef(ps, qs);
     float a = __fmul_rn(__fadd_rn(nf, 1.0f), s);
-    float pk = __expf(__fmul_rn(nf, log1pf(-ps)));  // P(X = 0) = q^n, n ps < 10 so >= e^-10.4
+    float pk = __expf(__fmul_rn(nf, log1pf(-ps)));  // P(X = 0) = q^n; n ps < 30 and ps <= 1/2, so >= e^-42
     float u = u01f(r.x);
     uint32_t k = 0;
-    const uint32_t kmax = n < 128u ? n : 128u;
+    const uint32_t kmax = n < 192u ? n : 192u;
     while (u > pk && k < kmax) {
       u = __fadd_rn(u, -pk);
       ++k;

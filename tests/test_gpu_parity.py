@@ -103,7 +103,8 @@ def test_log_gamma_carries_tiny_shapes(L):
 @pytest.mark.parametrize("n_trials,p", [(1, 0.5), (10, 0.3), (50, 0.5), (1000, 0.001), (1000, 0.3), (100, 0.97),
                                         (20, 0.5), (40, 0.25), (10**6, 0.4), (10**6, 9.9e-6), (10**6, 1.2e-5),
                                         (4_000_000_000, 0.5), (3_000_000_000, 1e-9), (12345, 0.9991), (37, 0.0),
-                                        (37, 1.0), (200, 0.05), (200, 0.06)])
+                                        (37, 1.0), (200, 0.05), (200, 0.06), (1000, 0.028), (1000, 0.031), (10**6, 2.9e-5),
+                                        (58, 0.5), (62, 0.5), (5000, 0.994)])
 def test_binomial_variates_match_the_binomial_law(L, n_trials, p):
     """Counterpart of std::binomial_distribution in distributions.cpp:45-46: chi-square against the exact pmf
     (p > 1e-4) and mean within 5 standard errors."""
