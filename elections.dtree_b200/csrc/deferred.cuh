@@ -291,9 +291,11 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
   }
   __syncwarp();
   uint32_t eliminated = 0, tie_rounds = 0, my_order = 0xFFu, q_head = 0, hw_queue = 0, hw_big = 0;
-  deferred_drain<LOG>(a, wt, ws, sc, cp, q_head, hw_queue, hw_big, eliminated, log_dp_max, key, stat);
 
-  for (uint32_t round = 0; round < n_rounds && !ws.overflow; ++round) {
+  // Pass -1 splits the root; pass r >= 0 eliminates a candidate, then splits what was parked under it.
+  for (int pass = -1; pass < (int)n_rounds && !ws.overflow; ++pass) {
+    if (pass >= 0) {
+    const uint32_t round = (uint32_t)pass;
     // candidates with the minimal tally among those standing (irv_ballot.cpp:88-98), one lane each
     const bool standing = lane < (int)nc && !(eliminated >> lane & 1u);
     const uint32_t t = standing ? ws.tally[lane] : 0xFFFFFFFFu;
@@ -340,6 +342,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
       }
     }
     __syncwarp();
+    }  // pass >= 0
     deferred_drain<LOG>(a, wt, ws, sc, cp, q_head, hw_queue, hw_big, eliminated, log_dp_max, key, stat);
   }
   __syncwarp();

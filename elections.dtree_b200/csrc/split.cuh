@@ -103,9 +103,8 @@ __device__ __forceinline__ void warp_tally_add(uint32_t *s_tally, bool valid, ui
 
 // i-th (0-based) candidate not in `used`, ascending.
 __device__ __forceinline__ uint32_t nth_unused(uint32_t used, uint32_t nc, uint32_t i) {
-  uint32_t avail = ~used & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
-  for (uint32_t k = 0; k < i; ++k) avail &= avail - 1u;
-  return (uint32_t)__ffs(avail) - 1u;
+  const uint32_t avail = ~used & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+  return __fns(avail, 0u, (int)i + 1);
 }
 
 // First standing preference of a ballot: scans from the front, skipping eliminated candidates.

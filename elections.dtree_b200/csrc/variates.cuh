@@ -23,6 +23,18 @@ namespace dtb {
 // even in double (the reference then falls back to a uniform one-hot, distributions.cpp:69-77);
 // carrying the logarithm keeps the exact alpha -> 0 limit and needs no fallback.
 // One Philox block per attempt: x from (r.x, r.y) by Box-Muller, u = r.z, boost uniform = r.w.
+// The exact Marsaglia-Tsang acceptance test, log u < x^2/2 + d (1 - v + log v), in double: the float
+// form cancels catastrophically for large d. Reached by a few percent of the draws only, so it lives
+// out of line (one copy in the kernel instead of one per call site: the kernels are I-cache bound).
+static __device__ __noinline__ bool gamma_accept_exact(float c, float x, float d, float u) {
+  double t = __dmul_rn((double)c, (double)x);
+  double vd = __dadd_rn(1.0, t);
+  vd = __dmul_rn(__dmul_rn(vd, vd), vd);
+  double x2 = __dmul_rn((double)x, (double)x);
+  double rhs = __fma_rn((double)d, __dadd_rn(__dadd_rn(1.0, -vd), log(vd)), __dmul_rn(0.5, x2));
+  return log((double)u) < rhs;
+}
+
 template <bool LOG>
 __device__ __forceinline__ float gamma_variate(float alpha, RngKey key, uint64_t node_key, uint32_t slot,
                                                uint32_t &attempts) {
@@ -44,12 +56,7 @@ __device__ __forceinline__ float gamma_variate(float alpha, RngKey key, uint64_t
     float u = u01f(r.z);
     float x2 = __fmul_rn(x, x);
     if (u < __fmaf_rn(-0.0331f, __fmul_rn(x2, x2), 1.0f)) break;
-    // exact test in double: for large d the float form of d(1 - v + log v) cancels catastrophically
-    double t = __dmul_rn((double)c, (double)x);
-    double vd = __dadd_rn(1.0, t);
-    vd = __dmul_rn(__dmul_rn(vd, vd), vd);
-    double rhs = __fma_rn((double)d, __dadd_rn(__dadd_rn(1.0, -vd), log(vd)), __dmul_rn(0.5, (double)x2));
-    if (log((double)u) < rhs) break;
+    if (gamma_accept_exact(c, x, d, u)) break;
     if (attempt > 64u) break;  // unreachable in practice (acceptance > 0.95); bounds the loop
   }
   float g = __fmul_rn(d, v);
@@ -64,14 +71,29 @@ __device__ __forceinline__ float gamma_variate(float alpha, RngKey key, uint64_t
 
 // ---------------------------------------------------------------------------------------------
 // Stirling tail fc(k) = log(k!) - [ (k+1/2) log(k+1) - (k+1) + log(2 pi)/2 ]  (Hörmann 1993).
-__device__ const double kStirlingTail[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983,
+static __device__ const double kStirlingTail[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983,
                                              0.02079067210376509, 0.0166446911898211, 0.0138761288230707,
                                              0.0118967099458917, 0.0104112652619720, 0.00925546218271273,
                                              0.00833056343336287};
-__device__ __forceinline__ double stirling_tail(double k) {
+static __device__ __noinline__ double stirling_tail(double k) {
   if (k <= 9.0) return kStirlingTail[(int)k];
   double kp1sq = (k + 1.0) * (k + 1.0);
   return (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / (k + 1.0);
+}
+
+// BTRS acceptance test for candidate k (Hörmann 1993, step 3.2), out of line for the same reason.
+static __device__ __noinline__ bool btrs_accept(double nd, double p, double spq, double b, double a, double us, double v,
+                                         double kd) {
+  const double q = 1.0 - p;
+  const double alpha = (2.83 + 5.1 / b) * spq;
+  const double rr = p / q;
+  const double m = floor((nd + 1.0) * p);
+  const double lhs = log(v * alpha / (a / (us * us) + b));
+  const double ub = (m + 0.5) * log((m + 1.0) / (rr * (nd - m + 1.0))) +
+                    (nd + 1.0) * log((nd - m + 1.0) / (nd - kd + 1.0)) +
+                    (kd + 0.5) * log(rr * (nd - kd + 1.0) / (kd + 1.0)) + stirling_tail(m) + stirling_tail(nd - m) -
+                    stirling_tail(kd) - stirling_tail(nd - kd);
+  return lhs <= ub;
 }
 
 // Binomial(n, ps) for ps <= 1/2, exact.
@@ -108,7 +130,7 @@ __device__ __forceinline__ uint32_t binomial_small_p(uint32_t n, float ps, RngKe
   for (uint32_t attempt = 0;; ++attempt) {
     U4 r = node_random(key, node_key, kStreamBinomial + slot, attempt);
     ++attempts;
-#pragma unroll
+#pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       double u = u01d(half ? r.z : r.x) - 0.5;
       double v = u01d(half ? r.w : r.y);
@@ -116,15 +138,7 @@ __device__ __forceinline__ uint32_t binomial_small_p(uint32_t n, float ps, RngKe
       double kd = floor((2.0 * a / us + b) * u + c);
       if (us >= 0.07 && v <= vr) return (uint32_t)kd;
       if (kd < 0.0 || kd > nd) continue;
-      double alpha = (2.83 + 5.1 / b) * spq;
-      double rr = p / q;
-      double m = floor((nd + 1.0) * p);
-      double lhs = log(v * alpha / (a / (us * us) + b));
-      double ub = (m + 0.5) * log((m + 1.0) / (rr * (nd - m + 1.0))) +
-                  (nd + 1.0) * log((nd - m + 1.0) / (nd - kd + 1.0)) +
-                  (kd + 0.5) * log(rr * (nd - kd + 1.0) / (kd + 1.0)) + stirling_tail(m) +
-                  stirling_tail(nd - m) - stirling_tail(kd) - stirling_tail(nd - kd);
-      if (lhs <= ub) return (uint32_t)kd;
+      if (btrs_accept(nd, p, spq, b, a, us, v, kd)) return (uint32_t)kd;
     }
     if (attempt > 256u) return (uint32_t)(nd * p);  // unreachable in practice
   }
