@@ -252,7 +252,8 @@ def main():
         ms = float(ms.item())
         assert int(total.sum().item()) == n_el * world * steps
         return {"value": n_el * world * steps / (ms / 1e3), "elapsed_ms": ms, "steps": steps, "elections_per_gpu": n_el,
-                "kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in kernel_ev])), "stats": st,
+                "kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in kernel_ev])),
+                "kernel_ms_steps": [round(a.elapsed_time(b), 2) for a, b in kernel_ev], "stats": st,
                 "kernel": "deferred_kernel" if st["mode"] == 1 else "simulate_kernel"}
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -339,7 +340,8 @@ def main():
         ach = b_alg * m["elections_per_gpu"] / (m["kernel_ms"] / 1e3) / 1e9
         return {"kernel": m["kernel"], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_election": b_alg,
-                "kernel_ms_per_launch": m["kernel_ms"], "elections_per_launch": m["elections_per_gpu"]}
+                "kernel_ms_per_launch": m["kernel_ms"], "kernel_ms_steps": m["kernel_ms_steps"],
+                "elections_per_launch": m["elections_per_gpu"]}
 
     rl = roofline(main)
     rl["denominators"] = denominators

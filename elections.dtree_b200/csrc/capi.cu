@@ -134,7 +134,8 @@ struct dtree {
     uint32_t n_sample = 0, urn_max = 0, min_depth = 0, max_depth = 0;
     double a0 = 0;
     bool vd = false, use_obs = false;
-    uint32_t pool = 0, queue = 0, big = 0;
+    uint32_t pool = 0, queue = 0, big = 0;              // largest usage seen (items)
+    uint32_t cap_pool = 0, cap_queue = 0, cap_big = 0;  // capacities in force
   } sizing;
   // tuning
   int block_threads = 0, blocks_per_sm = 0;
@@ -474,9 +475,14 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
       z.a0 = P.a0; z.vd = P.vd; z.use_obs = use_obs;
       z.pool = u[0]; z.queue = u[1]; z.big = u[2];
     }
-    pl.cap_items = (uint32_t)std::min<uint64_t>(pl.arena_items, 4ull * z.pool + 4096);
-    pl.cap_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 4ull * z.queue + 4096);
-    pl.cap_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 4ull * z.big + 1024);
+    // Capacities get a 4x margin over the largest election seen and are only revised when an election has
+    // used more than half of them (so that a new maximum does not reallocate the scratch every time).
+    if (!hit || 2ull * z.pool > z.cap_pool) z.cap_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 4ull * z.pool + 4096);
+    if (!hit || 2ull * z.queue > z.cap_queue) z.cap_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 4ull * z.queue + 4096);
+    if (!hit || 2ull * z.big > z.cap_big) z.cap_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 4ull * z.big + 1024);
+    pl.cap_items = std::min(z.cap_pool, pl.arena_items);
+    pl.cap_queue = std::min(z.cap_queue, pl.arena_queue);
+    pl.cap_big = std::min(z.cap_big, pl.arena_big);
     shape_deferred(t, n_elections - pilot_done, pl);
   }
   CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));

@@ -312,6 +312,10 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
     if (lane == (int)round) my_order = chosen;
     eliminated |= 1u << chosen;
     if (mn == 0u) continue;  // nobody counts for this candidate: nothing is parked under it
+    // After the last elimination nobody reads the tallies again (R_tree.cpp:245-253 only needs who is left), so
+    // the loser's ballots are not redistributed. The reference does redistribute them (irv_ballot.cpp:109-133) -
+    // typically the runner-up's whole subtree - without any effect on its output.
+    if (round + 1u == n_rounds) continue;
     // queue the nodes parked under the eliminated candidate: scan the holder bytes 16 per lane
     if (lane == 0 && ws.n_free < 0) ws.n_free = 0;
     __syncwarp();

@@ -361,6 +361,9 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
     const bool any = sm.tally[chosen] != 0u;
     __syncthreads();
     if (!any) continue;  // nobody holds ballots for this candidate: nothing to redistribute
+    // After the last elimination nobody reads the tallies again, so the loser's ballots stay where they are
+    // (the reference redistributes them, irv_ballot.cpp:109-133, without any effect on its output).
+    if (round + 1u == n_rounds) continue;
     // redistribution (irv_ballot.cpp:109-133): scan the holder bytes 16 at a time; only the entries
     // held by the eliminated candidate are re-examined
     const uint32_t pattern = chosen * 0x01010101u;
