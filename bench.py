@@ -5,7 +5,7 @@
 
 A *step* is one pass of the hot path (Dirichlet-tree posterior draw -> IRV -> win counts) over one
 batch of simulated elections of the named configuration, `--elections-per-gpu` per GPU (weak
-scaling: at 8 GPUs the default C3 step is exactly BASELINE's "100k elections sharded over 8 GPUs").
+scaling; the default C3 step is BASELINE's 100k elections on every GPU).
 Ranks simulate disjoint global election ranges, then all-reduce the <=32 win counts (NCCL).
 
  value      tree already resident in HBM, win counts left on the device; CUDA events on the launch
@@ -33,7 +33,7 @@ from __graft_entry__ import load_pkg  # noqa: E402
 
 METRIC = "simulated IRV elections/sec"
 SEED = "BENCHSEEDx"
-DEFAULT_EPG = {"C1": 1_000_000, "C2": 400_000, "C3": 12_500, "C4": 2_000, "C5": 100_000}
+DEFAULT_EPG = {"C1": 4_000_000, "C2": 1_000_000, "C3": 100_000, "C4": 4_000, "C5": 200_000}
 
 
 def describe(name, cfg, epg):
@@ -82,7 +82,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + self.QUERY,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass

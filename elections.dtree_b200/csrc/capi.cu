@@ -111,8 +111,11 @@ struct dtree {
   int sm_count = 0;
   size_t smem_optin = 0;
   // device mirror
-  uint64_t mirrored_version = ~0ull;
+  uint64_t mirrored_version = ~0ull, image_version = ~0ull;
   FlatTree flat;
+  std::vector<uint64_t> h_obs_keys;
+  std::vector<uint8_t> h_obs_first;
+  std::vector<uint32_t> h_obs_tally0;
   DevBuf<uint32_t> d_node_base, d_node_total, d_slot_count, d_obs_cnt, d_obs_tally0;
   DevBuf<int32_t> d_slot_child;
   DevBuf<uint8_t> d_slot_cand, d_obs_first;
@@ -168,39 +171,49 @@ DeviceParams device_params(const HostParams &P) {
   return D;
 }
 
-int ensure_mirror(dtree *t, cudaStream_t s) {
-  if (t->mirrored_version == t->tree.version()) return DTREE_OK;
+// Host image of the device mirror: the CSR arrays plus the packed observed entries. Rebuilt only when the
+// tree changes; dtree_invalidate_device drops the device copy but keeps this, so re-mirroring is a plain upload.
+int ensure_host_image(dtree *t) {
+  if (t->image_version == t->tree.version()) return DTREE_OK;
   t->tree.flatten(t->flat);
   const FlatTree &F = t->flat;
   const uint32_t nc = t->tree.P.nc;
   const int W = key_words_for(nc);
   if (F.slot_count.size() >= 0xFFFFFFF0ull) return fail(DTREE_ERR_STATE, "tree has too many outcome slots for 32-bit indices");
+  size_t n = F.obs_counts.size();
+  t->h_obs_keys.assign(n * W, 0);
+  t->h_obs_first.assign(n, 0);
+  t->h_obs_tally0.assign(kMaxCandidates, 0);
+  for (size_t i = 0; i < n; ++i) {
+    uint64_t k[kMaxKeyWords];
+    uint32_t len = (uint32_t)(F.obs_offsets[i + 1] - F.obs_offsets[i]);
+    pack_ballot(F.obs_prefs.data() + F.obs_offsets[i], len, nc, true, k, nullptr);
+    for (int w = 0; w < W; ++w) t->h_obs_keys[i * W + w] = k[w];
+    t->h_obs_first[i] = len ? F.obs_prefs[F.obs_offsets[i]] : 0xFF;
+    if (len) t->h_obs_tally0[t->h_obs_first[i]] += F.obs_counts[i];
+  }
+  t->image_version = t->tree.version();
+  return DTREE_OK;
+}
+
+int ensure_mirror(dtree *t, cudaStream_t s) {
+  if (t->mirrored_version == t->tree.version()) return DTREE_OK;
+  int rc = ensure_host_image(t);
+  if (rc) return rc;
+  const FlatTree &F = t->flat;
   CUDA_TRY(t->d_node_base.upload(F.node_base, s));
   CUDA_TRY(t->d_node_total.upload(F.node_total, s));
   CUDA_TRY(t->d_slot_count.upload(F.slot_count, s));
   CUDA_TRY(t->d_slot_child.upload(F.slot_child, s));
   CUDA_TRY(t->d_slot_cand.upload(F.slot_cand, s));
-  // observed entries for the IRV stage
-  size_t n = F.obs_counts.size();
-  std::vector<uint64_t> keys(n * W);
-  std::vector<uint8_t> first(n);
-  std::vector<uint32_t> tally0(kMaxCandidates, 0);
-  for (size_t i = 0; i < n; ++i) {
-    uint64_t k[kMaxKeyWords];
-    uint32_t len = (uint32_t)(F.obs_offsets[i + 1] - F.obs_offsets[i]);
-    pack_ballot(F.obs_prefs.data() + F.obs_offsets[i], len, nc, true, k, nullptr);
-    for (int w = 0; w < W; ++w) keys[i * W + w] = k[w];
-    first[i] = len ? F.obs_prefs[F.obs_offsets[i]] : 0xFF;
-    if (len) tally0[first[i]] += F.obs_counts[i];
-  }
-  CUDA_TRY(t->d_obs_key.upload(keys, s));
+  CUDA_TRY(t->d_obs_key.upload(t->h_obs_keys, s));
   CUDA_TRY(t->d_obs_cnt.upload(F.obs_counts, s));
-  CUDA_TRY(t->d_obs_first.upload(first, s));
-  CUDA_TRY(t->d_obs_tally0.upload(tally0, s));
-  t->n_obs_entries = (uint32_t)n;
-  t->stats[8] += (F.node_base.size() + F.node_total.size() + F.slot_count.size() + F.slot_child.size()) * 4 + F.slot_cand.size() +
-                 keys.size() * 8 + n * 5 + kMaxCandidates * 4;
-  CUDA_TRY(cudaStreamSynchronize(s));  // the host vectors above die with this frame
+  CUDA_TRY(t->d_obs_first.upload(t->h_obs_first, s));
+  CUDA_TRY(t->d_obs_tally0.upload(t->h_obs_tally0, s));
+  t->n_obs_entries = (uint32_t)F.obs_counts.size();
+  t->stats[8] += (F.node_base.size() + F.node_total.size() + F.slot_count.size() + F.slot_child.size()) * 4 +
+                 F.slot_cand.size() + t->h_obs_keys.size() * 8 + F.obs_counts.size() * 5 + kMaxCandidates * 4;
+  CUDA_TRY(cudaStreamSynchronize(s));  // pageable sources: the copies must not outlive a later update
   t->mirrored_version = t->tree.version();
   return DTREE_OK;
 }
@@ -384,12 +397,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   const uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->tree.n_observed();
   Plan pl;
   pl.deferred = t->mode == 1;
-  if (t->mode < 0) {
-    // Tiny ballot spaces (a few dozen prefixes) are cheaper to enumerate than to park and re-visit.
-    double prefixes = 0;
-    for (uint32_t l = 0; l < nc; ++l) prefixes += falling_factorial(nc, l);
-    pl.deferred = prefixes > 256.0;
-  }
+  if (t->mode < 0) pl.deferred = true;  // the deferred kernel is the faster one on every configuration measured
   if (pl.deferred) {
     rc = make_plan_deferred(t, n_sample, n_elections, pl);
     if (rc) return rc;

@@ -90,7 +90,7 @@ __device__ __forceinline__ void enqueue_node(const SimArgs &a, DeferredWarp &ws,
 // Routes the ballots of one child of a node that has just been split. May be called by any subset of
 // lanes (divergent code). `tot` ballots now have `cand` as their next preference; `cs` of them are
 // sampled ballots that continue below the child, `child` is the child's CSR node (-1: none).
-__device__ __forceinline__ void route_child(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
+static __device__ __noinline__ void route_child(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
                                             const DeferredCaps &cp, const DItem &x, uint32_t depth, uint32_t eliminated, uint32_t cand,
                                             uint32_t tot, uint32_t cs, int32_t child, bool has_obs, int big_sel) {
   const bool standing = !(eliminated >> cand & 1u);
@@ -144,12 +144,14 @@ __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp 
   if (nb != 0xFFFFFFFFu && a.use_obs) {
     // initialised node carrying observed ballots: every child slot may have something to route
     uint64_t c4[2] = {0ull, 0ull};  // 4-bit count per slot (count <= 8)
+#pragma unroll 1
     for (uint32_t b = 0; b < x.count; ++b) {
       const uint32_t s = (uint32_t)(picks >> (8u * b)) & 0xFFu;
       if (s == lv.K) continue;  // the ballot stops here: exhausted
       c4[s >> 4] += 1ull << (4u * (s & 15u));
     }
     stat[kStatSlots] += lv.d;
+#pragma unroll 1
     for (uint32_t slot = 0; slot < lv.K; ++slot) {
       const uint32_t c = (uint32_t)(c4[slot >> 4] >> (4u * (slot & 15u))) & 15u;
       const uint32_t obs = a.T.slot_count[nb + slot];
@@ -160,10 +162,12 @@ __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp 
   } else {
     // prior-only subtree (or sampling with replacement): only the drawn outcomes matter
     uint32_t done = 0;
+#pragma unroll 1
     for (uint32_t b = 0; b < x.count; ++b) {
       if (done >> b & 1u) continue;
       const uint32_t slot = (uint32_t)(picks >> (8u * b)) & 0xFFu;
       uint32_t c = 1;
+#pragma unroll 1
       for (uint32_t b2 = b + 1; b2 < x.count; ++b2)
         if (((uint32_t)(picks >> (8u * b2)) & 0xFFu) == slot) {
           ++c;
@@ -291,6 +295,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
   }
   __syncwarp();
   uint32_t eliminated = 0, tie_rounds = 0, my_order = 0xFFu, q_head = 0, hw_queue = 0, hw_big = 0;
+  const bool early_stop = a.n_winners == 1u && a.elim_orders == nullptr;
 
   // Pass -1 splits the root; pass r >= 0 eliminates a candidate, then splits what was parked under it.
   for (int pass = -1; pass < (int)n_rounds && !ws.overflow; ++pass) {
@@ -298,6 +303,17 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
     const uint32_t round = (uint32_t)pass;
     // candidates with the minimal tally among those standing (irv_ballot.cpp:88-98), one lane each
     const bool standing = lane < (int)nc && !(eliminated >> lane & 1u);
+    if (early_stop) {
+      // A candidate holding more than half of the ballots still in play can never have the minimal tally
+      // again (tallies only grow, ballots in play only shrink), so it is the winner: stop here.
+      const uint32_t mine = standing ? ws.tally[lane] : 0u;
+      const uint32_t total = __reduce_add_sync(0xffffffffu, mine), top = __reduce_max_sync(0xffffffffu, mine);
+      if (top > total - top) {
+        const uint32_t who = __ballot_sync(0xffffffffu, standing && mine == top);
+        eliminated = ~who & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+        break;
+      }
+    }
     const uint32_t t = standing ? ws.tally[lane] : 0xFFFFFFFFu;
     const uint32_t mn = __reduce_min_sync(0xffffffffu, t);
     uint32_t tied = __ballot_sync(0xffffffffu, standing && t == mn);

@@ -73,7 +73,13 @@ DT_HD RngKey election_key(uint64_t seed, uint64_t election) {
   return k;
 }
 
-DT_HD U4 node_random(RngKey k, uint64_t node_key, uint32_t stream, uint32_t attempt) {
+// Out of line on the device: every variate calls it, and one copy instead of one per call site keeps the
+// kernels' hot code inside the instruction cache (they were I-cache bound with it inlined).
+#if defined(__CUDACC__)
+static __device__ __noinline__ U4 node_random(RngKey k, uint64_t node_key, uint32_t stream, uint32_t attempt) {
+#else
+inline U4 node_random(RngKey k, uint64_t node_key, uint32_t stream, uint32_t attempt) {
+#endif
   U4 c;
   c.x = (uint32_t)node_key;
   c.y = (uint32_t)(node_key >> 32);

@@ -61,7 +61,7 @@ struct SharedFixed {
   // IRV
   uint32_t tally[kMaxCandidates];
   uint32_t wins[kMaxCandidates];
-  uint32_t eliminated, chosen, tie_rounds;
+  uint32_t eliminated, chosen, tie_rounds, decided;
   uint32_t election;
   uint8_t order[kMaxCandidates];
 };
@@ -338,11 +338,21 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
     if (tid == 0) {
       // candidates with the minimal tally among those standing (irv_ballot.cpp:88-98)
       uint32_t elim = sm.eliminated, mn = 0xFFFFFFFFu, tied = 0, ntied = 0;
+      uint32_t total = 0, top = 0, top_c = 0;
       for (uint32_t c = 0; c < nc; ++c) {
         if (elim >> c & 1u) continue;
         uint32_t t = sm.tally[c];
         if (t < mn) { mn = t; tied = 1u << c; ntied = 1; }
         else if (t == mn) { tied |= 1u << c; ++ntied; }
+        total += t;
+        if (t > top) { top = t; top_c = c; }
+      }
+      // A candidate holding more than half of the ballots still in play can never have the minimal tally
+      // again (tallies only grow, ballots in play only shrink), so it is the winner: stop here.
+      sm.decided = 0;
+      if (a.n_winners == 1u && a.elim_orders == nullptr && top > total - top) {
+        sm.eliminated = ~(1u << top_c) & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+        sm.decided = 1;
       }
       uint32_t pick = 0;
       if (ntied > 1) {  // uniform among the tied, ascending index (irv_ballot.cpp:100-102)
@@ -354,9 +364,10 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
       uint32_t chosen = (uint32_t)__ffs(tied) - 1u;
       sm.chosen = chosen;
       sm.order[round] = (uint8_t)chosen;
-      sm.eliminated = elim | (1u << chosen);
+      if (!sm.decided) sm.eliminated = elim | (1u << chosen);
     }
     __syncthreads();
+    if (sm.decided) break;
     const uint32_t chosen = sm.chosen, eliminated = sm.eliminated;
     const bool any = sm.tally[chosen] != 0u;
     __syncthreads();

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(256) irv_only_kernel(const IrvArgs ia) {
   SimArgs a;  // only the fields irv_election reads
   a.P.nc = ia.nc;
   a.n_obs = 0;
+  a.n_winners = 0;  // 0: never stop early, dtree_irv wants the whole order
+  a.elim_orders = nullptr;
   a.obs_key = nullptr;
   a.obs_cnt = nullptr;
   a.obs_first = nullptr;

@@ -162,7 +162,7 @@ __device__ __forceinline__ uint32_t coalesced_reserve(uint32_t *cursor) {
 // probability b / (A + b), else draws a fresh outcome with probability alpha_i / A. Exactly
 // Dirichlet-multinomial(count, alpha); no Gamma or binomial variates. Returns the outcome of
 // ball b in bits [8b, 8b+8).
-__device__ __forceinline__ uint64_t urn_picks(const SimArgs &a, const LevelInfo &lv, int32_t node, uint32_t nbase,
+static __device__ __noinline__ uint64_t urn_picks(const SimArgs &a, const LevelInfo &lv, int32_t node, uint32_t nbase,
                                               uint32_t count, const RngKey key, uint64_t node_key) {
   const uint32_t d = lv.d;
   float A;
@@ -175,6 +175,7 @@ __device__ __forceinline__ uint64_t urn_picks(const SimArgs &a, const LevelInfo 
   }
   uint64_t picks = 0;
   U4 r;
+#pragma unroll 1
   for (uint32_t b = 0; b < count; ++b) {
     if ((b & 3u) == 0u) r = node_random(key, node_key, kStreamUrn, b >> 2);
     const uint32_t bits = (b & 3u) == 0u ? r.x : (b & 3u) == 1u ? r.y : (b & 3u) == 2u ? r.z : r.w;
@@ -191,6 +192,7 @@ __device__ __forceinline__ uint64_t urn_picks(const SimArgs &a, const LevelInfo 
       } else if (nbase != 0xFFFFFFFFu) {
         float acc = 0.0f;
         pick = 0u;  // on fall-through (rounding): the last outcome with a positive parameter
+#pragma unroll 1
         for (uint32_t i = 0; i < d; ++i) {
           const float al = __fadd_rn((float)a.T.slot_count[nbase + i], lv.a_prior);
           acc = __fadd_rn(acc, al);

@@ -164,8 +164,8 @@ int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user
 /* ---- tuning / introspection (not part of the reference interface) ----------------------------
  * key: "mode" — how dtree_sample_posterior* simulates an election: 1 expands a tree node only when IRV
  *        needs to look below it; 0 materialises every sampled ballot first, as the reference does
- *        (dirichlet_tree.h:216-235 then irv_ballot.cpp:42-138); -1 (default) picks 0 for ballot spaces of
- *        at most 256 prefixes and 1 otherwise. Both give bit-identical outcomes;
+ *        (dirichlet_tree.h:216-235 then irv_ballot.cpp:42-138); -1 (default) picks 1 unless its worst-case
+ *        scratch does not fit the device. Both give bit-identical outcomes;
  *      "block_threads" (0 = auto), "blocks_per_sm" (0 = auto), "urn_max" (largest count split by the
  *        Polya-urn shortcut instead of Gamma variates, <= 8).
  * Returns DTREE_ERR_ARG for an unknown key. */
