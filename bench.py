@@ -126,7 +126,7 @@ def run_reference(args, cfg, name):
     oracle, olib, kind = load_oracle()
     threads = host_threads()
     prefs, offsets = pkg_wl.observed_ballots(name)
-    per_step = max(2 * threads, cpu_sample_size(cfg, threads) // 4)
+    per_step = max(4 * threads, cpu_sample_size(cfg, threads) // 2)
     t = olib.tree(cfg["n_candidates"], cfg["min_depth"], cfg["max_depth"], cfg["a0"], cfg["vd"])
     t.update((prefs, offsets))
     secs = []
@@ -306,12 +306,18 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     # the kernel's own per-election counters (exact for what was launched)
-    S_k = stats["slots"] / max(stats["elections"], 1)
-    E_k = stats["entries"] / max(stats["elections"], 1) + (len(t.observed_indices()[2]))
-    R_k = stats["irv_rereads"] / max(stats["elections"], 1)
+    # the materialising kernel's own counters when it ran (S, E, R describe materialisation), else the headline's
+    mst = stats
+    for cand in (main, other):
+        if cand is not None and cand["kernel"] == "simulate_kernel":
+            mst = cand["stats"]
+    S_k = mst["slots"] / max(mst["elections"], 1)
+    E_k = mst["entries"] / max(mst["elections"], 1) + (len(t.observed_indices()[2]))
+    R_k = mst["irv_rereads"] / max(mst["elections"], 1)
     cpu_baseline = None
     b_alg = 4 * S_k + 32 * E_k + 16 * R_k + 8 * nc
-    denominators = {"source": "kernel counters", "S": S_k, "E": E_k, "R": R_k}
+    denominators = {"source": "simulate_kernel counters" if mst["mode"] == 0 else "deferred_kernel counters (not 8(d)'s)",
+                    "S": S_k, "E": E_k, "R": R_k}
     if not args.no_cpu_baseline:
         oracle, olib, kind = load_oracle()
         port = oracle.load("port")
@@ -336,20 +342,43 @@ def main():
         _, secs = cpu_run(olib, cfg, prefs, offsets, n_cpu, threads, SEED)
         cpu_baseline = {"value": n_cpu / secs, "unit": "elections/s", "cores": threads, "kind": kind,
                         "sample": "%d elections of the same workload in %.1f s, %d threads (R_tree.cpp:213-242 pool)" % (n_cpu, secs, threads)}
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except (OSError, ValueError):
+        traffic_tab = {}
+
     def roofline(m):
-        ach = b_alg * m["elections_per_gpu"] / (m["kernel_ms"] / 1e3) / 1e9
-        return {"kernel": m["kernel"], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_election": b_alg,
-                "kernel_ms_per_launch": m["kernel_ms"], "kernel_ms_steps": m["kernel_ms_steps"],
-                "elections_per_launch": m["elections_per_gpu"]}
+        """algorithmic bytes per launch / CUDA-event duration of the launch, against measured HBM copy
+        bandwidth. The materialising kernel moves 8(d)'s bytes (B_alg = 4S + 32E + 16R + 8nc). The deferred kernel
+        never creates most of them, so it is rated on the bytes ITS algorithm must move (4 B per outcome slot read +
+        a 32 B node record written and read once per node split + 8nc); the 8(d) rate is kept beside it."""
+        n_el, secs = m["elections_per_gpu"], m["kernel_ms"] / 1e3
+        st = m["stats"]
+        per_el = max(st["elections"], 1)
+        if m["kernel"] == "simulate_kernel":
+            bytes_el = b_alg
+        else:
+            bytes_el = 4.0 * st["slots"] / per_el + 64.0 * st["items"] / per_el + 8 * nc
+        ach = bytes_el * n_el / secs / 1e9
+        tr = traffic_tab.get(m["kernel"], {})
+        out = {"kernel": m["kernel"], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+               "traffic": tr["bytes_per_election"] * n_el if tr.get("config") == name else None,
+               "traffic_source": tr.get("capture") if tr.get("config") == name else None,
+               "peak_source": peak_src, "algorithmic_bytes_per_election": bytes_el,
+               "kernel_ms_per_launch": m["kernel_ms"], "kernel_ms_steps": m["kernel_ms_steps"],
+               "elections_per_launch": n_el}
+        if m["kernel"] == "deferred_kernel":
+            eq = b_alg * n_el / secs / 1e9
+            out["survey_8d"] = {"bytes_per_election": b_alg, "equivalent_GBps": eq, "equivalent_frac": eq / peak,
+                                "note": "what a kernel that materialises every ballot would have to move for the same elections; "
+                                        "above 1.0 because this kernel provably never touches those bytes (it splits %.0f nodes per "
+                                        "election where a full expansion visits %.0f), not a bandwidth claim"
+                                        % (st["items"] / per_el, denominators.get("kernel_counters", {}).get("items_full", float("nan")))}
+            out["limiter"] = "instruction issue / divergence / I-cache, not HBM (profiles/r01d_ncu_deferred_kernel_c3.txt)"
+        return out
 
     rl = roofline(main)
     rl["denominators"] = denominators
-    if main["kernel"] == "deferred_kernel":
-        rl["note"] = ("algorithmic bytes are SURVEY 8(d)'s, i.e. what materialising every ballot moves; this kernel splits only "
-                      "the nodes IRV asks about (%.0f of the %.0f a full expansion visits) and writes no ballot list, so its "
-                      "DRAM traffic is far below them; see `materialised` for the kernel that does move them"
-                      % (stats["items"] / max(stats["elections"], 1), denominators.get("kernel_counters", {}).get("items_full", float("nan"))))
     line = {
         "metric": METRIC, "value": value, "unit": "elections/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
