@@ -531,3 +531,60 @@ def test_abort_callback_stops_a_run(pkg, L):
     assert ei.value.code == pkg._native.ERR_ABORTED and len(calls) == 2
     lib.dtree_set_abort_callback(dtree._h, C.cast(None, pkg._native.ABORT_CB), None)
     assert int(dtree.sample_posterior_counts(100, 50, seed="abort").sum()) == 100
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configurations at full size: size-independent properties
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["C2", "C3", "C4"])
+def test_full_size_configs_conserve_ballots_and_agree_across_kernels(pkg, L, name):
+    """At BASELINE.json's full shapes (6/10/20 candidates, 50 k / 1 M / 1 M ballots per election) the oracle is too
+    slow to replay, so the checks are the domain's invariants: a materialised election holds exactly n_ballots
+    ballots, every sampled ballot is a duplicate-free ranking of legal length listed once, the observed ballots are
+    all in it, win counts add up, and the two kernels agree election by election."""
+    W = pkg.workloads
+    cfg = W.CONFIGS[name]
+    nc = cfg["n_candidates"]
+    prefs, offsets = W.observed_ballots(name)
+    t = pkg.dirichlet_tree(names(pkg, nc), cfg["min_depth"], cfg["max_depth"], cfg["a0"], cfg["vd"], device=0)
+    t.update_indices(prefs, offsets)
+    n_obs = t.n_observed
+    p, off, cnt = t.posterior_set_indices(5, cfg["n_ballots"], False, "FULL")
+    assert int(cnt.astype(np.int64).sum()) == cfg["n_ballots"]
+    op, ooff, ocnt = t.observed_indices()
+    n_obs_entries = len(ocnt)
+    assert int(ocnt.astype(np.int64).sum()) == n_obs
+    assert np.array_equal(cnt[:n_obs_entries], ocnt) and np.array_equal(off[:n_obs_entries + 1], ooff)
+    lens = np.diff(off.astype(np.int64))[n_obs_entries:]
+    assert lens.min() >= cfg["min_depth"] and lens.max() <= min(cfg["max_depth"], nc - 1)
+    sampled = oracle.csr_to_ballots(p, off)[n_obs_entries:]
+    assert len(set(sampled)) == len(sampled) and all(len(set(b)) == len(b) for b in sampled[:20000])
+    n_el = {"C2": 3000, "C3": 400, "C4": 60}[name]
+    res = {}
+    for mode in (0, 1):
+        t.tune(mode=mode)
+        res[mode] = t.sample_posterior_counts(n_el, cfg["n_ballots"], seed="FULL", return_orders=True)
+        assert int(res[mode][0].sum()) == n_el
+        plain = t.sample_posterior_counts(n_el, cfg["n_ballots"], seed="FULL")  # with the early-stop short-cuts
+        assert plain.tolist() == res[mode][0].tolist()
+    assert res[0][0].tolist() == res[1][0].tolist() and np.array_equal(res[0][1], res[1][1])
+    # the order reported for election 5 is one the reference rule allows on election 5's ballots
+    ok, _ = oracle.load("port").irv_check_order((p, off), cnt, nc, res[1][1][5].astype(np.uint32))
+    assert ok
+
+
+@pytest.mark.parametrize("a0", [1e-4, 1e-2, 1.0, 10.0])
+def test_c5_dirichlet_special_case_calibration(pkg, L, port, a0):
+    """BASELINE config 5 (vd=TRUE, min_depth = max_depth = 7, 8 candidates, a0 sweep), reduced to sizes the oracle
+    finishes in seconds: posterior win probabilities, GPU vs oracle, within 4.5 sigma of the binomial Monte-Carlo
+    error of the difference. a0 = 1e-4 is where Gamma variates underflow in double and the reference falls back to
+    its one-hot (distributions.cpp:69-77); the log-space variates must land on the same probabilities."""
+    W = pkg.workloads
+    prefs, offsets = W.plackett_luce_ballots(8, 0.15, 120, 5, None)
+    t, o = make_pair(pkg, port, 8, 7, 7, a0, True, prefs, offsets)
+    n_el, n_b = 1500, 3000
+    gpu = t.sample_posterior_counts(n_el, n_b, seed="C5cal") / float(n_el)
+    freq, _ = o.sample_posterior(n_el, n_b, 1, False, 4, "C5cal")
+    pooled = (gpu + freq) / 2
+    tol = 4.5 * np.sqrt(np.maximum(pooled * (1 - pooled), 1.0 / n_el) * 2 / n_el)
+    assert np.all(np.abs(gpu - freq) <= tol), (a0, gpu.tolist(), freq.tolist())
