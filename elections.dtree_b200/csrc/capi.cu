@@ -440,10 +440,9 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
                      z.min_depth == P.min_depth && z.max_depth == P.max_depth && z.a0 == P.a0 && z.vd == P.vd &&
                      z.use_obs == use_obs;
     CUDA_TRY(t->d_arena.reserve(pl.arena_stride * pl.n_arenas));
-    if (t->d_locks.n < kMaxArenas) {
-      CUDA_TRY(t->d_locks.reserve(kMaxArenas));
-      CUDA_TRY(cudaMemsetAsync(t->d_locks.p, 0, kMaxArenas * sizeof(unsigned int), s));
-    }
+    // Arena locks start free at every call: a launch that died must not leave one held.
+    CUDA_TRY(t->d_locks.reserve(kMaxArenas));
+    CUDA_TRY(cudaMemsetAsync(t->d_locks.p, 0, kMaxArenas * sizeof(unsigned int), s));
     CUDA_TRY(t->d_usage.reserve(4));
     CUDA_TRY(cudaMemsetAsync(t->d_usage.p, 0, 4 * sizeof(unsigned int), s));
     if (!hit) {
