@@ -233,7 +233,7 @@ class dirichlet_tree:
         return {c: counts[i] / float(n_elections) for i, c in enumerate(self._candidates)}
 
     def sample_posterior_counts(self, n_elections, n_ballots, n_winners=1, replace=False, n_threads=None, seed=None,
-                                first_election=0, return_orders=False):
+                                first_election=0, return_orders=False, devices=None):
         if n_elections <= 0:
             raise ValueError("`n_elections` must be an integer > 0.")
         if n_ballots < self.n_observed and not replace:
@@ -244,6 +244,14 @@ class dirichlet_tree:
         seed = (gseed() if seed is None else seed).encode()
         nc = self.n_candidates
         wins = np.zeros(nc, dtype=np.uint64)
+        if devices is not None:  # one process, several GPUs (dtree_sample_posterior_multi)
+            if return_orders:
+                raise ValueError("elimination orders are only returned by single-device calls")
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            N.check(self._L.dtree_sample_posterior_multi(self._h, devs, len(devices), int(first_election),
+                                                         int(n_elections), int(n_ballots), int(n_winners), int(replace),
+                                                         seed, len(seed), wins.ctypes.data_as(N.u64p)))
+            return wins
         orders = np.zeros((int(n_elections), nc), dtype=np.uint8) if return_orders else None
         N.check(self._L.dtree_sample_posterior(self._h, int(first_election), int(n_elections), int(n_ballots),
                                                int(n_winners), int(replace), seed, len(seed),

@@ -144,6 +144,8 @@ struct dtree {
   int block_threads = 0, blocks_per_sm = 0;
   uint32_t urn_max = 8;
   int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
+  // replicas on other devices for dtree_sample_posterior_multi (owned; same parameters, tree copied when stale)
+  std::vector<dtree *> replicas;
   // callbacks, stats
   int (*should_abort)(void *) = nullptr;
   void *abort_user = nullptr;
@@ -663,6 +665,8 @@ int dtree_create(uint32_t nc, uint32_t min_depth, uint32_t max_depth, double a0,
 
 int dtree_destroy(dtree_t *t) {
   if (!t) return DTREE_OK;
+  for (dtree *r : t->replicas) dtree_destroy(r);
+  t->replicas.clear();
   if (t->sm_count) {
     DeviceGuard g(t->device);
     t->d_node_base.release(); t->d_node_total.release(); t->d_slot_count.release(); t->d_obs_cnt.release(); t->d_obs_tally0.release();
@@ -833,6 +837,64 @@ int dtree_sample_posterior_device(dtree_t *t, uint64_t first_election, uint32_t 
   if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
   return run_posterior(t, first_election, n_elections, n_ballots, n_winners, replace, seed, seed_len,
                        (unsigned long long *)d_win_counts, nullptr, (cudaStream_t)stream, false);
+}
+
+int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, uint64_t first_election,
+                                 uint32_t n_elections, uint32_t n_ballots, uint32_t n_winners, int replace,
+                                 const char *seed, size_t seed_len, uint64_t *win_counts) {
+  if (!t || !win_counts) return fail(DTREE_ERR_ARG, "null argument");
+  if (n_devices < 1 || n_devices > 64) return fail(DTREE_ERR_ARG, "n_devices must be in [1, 64]");
+  const int visible = dtree_device_count();
+  if (visible < 1) return fail(DTREE_ERR_CUDA, "no CUDA device available: libdtree_b200 has no CPU path");
+  const uint32_t nc = t->tree.P.nc;
+  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = 0;
+  // one replica per listed device; index i of `replicas` serves devices[i]
+  while ((int)t->replicas.size() < n_devices) t->replicas.push_back(nullptr);
+  std::vector<dtree *> used;
+  const uint32_t per = (uint32_t)(((uint64_t)n_elections + n_devices - 1) / n_devices);  // ceil, as sharding.py
+  int rc = DTREE_OK;
+  for (int i = 0; i < n_devices && rc == DTREE_OK; ++i) {
+    const int dev = devices ? devices[i] : i;
+    if (dev < 0 || dev >= visible) return fail(DTREE_ERR_ARG, "device %d does not exist (%d visible)", dev, visible);
+    dtree *&r = t->replicas[i];
+    if (r && r->device != dev) {
+      dtree_destroy(r);
+      r = nullptr;
+    }
+    if (!r) r = new dtree(t->tree.P, dev);
+    if (r->tree.version() != t->tree.version() || r->tree.n_observed() != t->tree.n_observed()) r->tree = t->tree;
+    r->tree.P = t->tree.P;
+    r->mode = t->mode;
+    r->urn_max = t->urn_max;
+    r->block_threads = t->block_threads;
+    r->blocks_per_sm = t->blocks_per_sm;
+    const uint64_t lo = std::min<uint64_t>(n_elections, (uint64_t)i * per), hi = std::min<uint64_t>(n_elections, lo + per);
+    if (hi == lo) continue;
+    rc = bind_device(r);
+    if (rc) break;
+    DeviceGuard g(r->device);
+    if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", r->device);
+    CUDA_TRY(r->d_wins.reserve(kMaxCandidates));
+    CUDA_TRY(cudaMemsetAsync(r->d_wins.p, 0, kMaxCandidates * sizeof(unsigned long long), 0));
+    rc = run_posterior(r, first_election + lo, (uint32_t)(hi - lo), n_ballots, n_winners, replace, seed, seed_len,
+                       r->d_wins.p, nullptr, 0, false);
+    used.push_back(r);
+  }
+  // collect (also on failure, so that nothing is left running)
+  for (dtree *r : used) {
+    DeviceGuard g(r->device);
+    int rc2 = dtree_sample_posterior_finish(r, nullptr);
+    unsigned long long w[kMaxCandidates];
+    if (rc2 == DTREE_OK && cudaMemcpy(w, r->d_wins.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc2 = fail(DTREE_ERR_CUDA, "reading win counts from device %d failed", r->device);
+    if (rc2 == DTREE_OK)
+      for (uint32_t c = 0; c < nc; ++c) win_counts[c] += w[c];
+    else if (rc == DTREE_OK)
+      rc = rc2;
+  }
+  t->stats[0] = used.size();
+  t->stats[1] = n_elections;
+  return rc;
 }
 
 int dtree_sample_posterior_finish(dtree_t *t, void *stream) {

@@ -140,14 +140,20 @@ class RDirichletTree {
     return out;
   }
 
-  // R_tree.cpp:177-257. nThreads is accepted and ignored: the elections run on the GPU.
+  // R_tree.cpp:177-257. nThreads is accepted and ignored: the reference's thread pool over elections
+  // (:200-242) becomes a pool over the visible GPUs, each taking a contiguous range of elections.
   Rcpp::NumericVector samplePosterior(unsigned nElections, unsigned nBallots, unsigned nWinners, bool replace,
                                       unsigned nThreads, std::string seed) {
     (void)nThreads;
     size_t nc = getNCandidates();
     std::vector<uint64_t> wins(nc, 0);
-    check(dtree_sample_posterior(tree, 0, nElections, nBallots, nWinners, replace ? 1 : 0, seed.data(), seed.size(),
-                                 wins.data(), nullptr));
+    int nDevices = dtree_device_count();
+    if (nDevices > 1)
+      check(dtree_sample_posterior_multi(tree, nullptr, nDevices, 0, nElections, nBallots, nWinners, replace ? 1 : 0,
+                                         seed.data(), seed.size(), wins.data()));
+    else
+      check(dtree_sample_posterior(tree, 0, nElections, nBallots, nWinners, replace ? 1 : 0, seed.data(), seed.size(),
+                                   wins.data(), nullptr));
     Rcpp::NumericVector out(nc);
     out.names() = candidateVector;
     for (size_t i = 0; i < nc; ++i) out[i] = (double)wins[i] / nElections;  // R_tree.cpp:255

@@ -123,6 +123,16 @@ int dtree_sample_posterior_device(dtree_t *t, uint64_t first_election, uint32_t 
                                   const char *seed, size_t seed_len, uint64_t *d_win_counts,
                                   void *stream);
 
+/* One process, several GPUs (what an R session on a multi-GPU host uses; the thread pool of
+ * R_tree.cpp:200-242 becomes a device pool). Elections [first_election, first_election + n_elections) are
+ * split into n_devices contiguous ranges; range i runs on CUDA device devices[i] (devices == NULL: ordinals
+ * 0..n_devices-1; a device may be listed more than once) against a replica of the tree mirrored there, all
+ * devices concurrently; the uint64 win counts are added on the host. Totals are bit-identical to a
+ * single-device call. win_counts [n_candidates] host, overwritten. */
+int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, uint64_t first_election,
+                                 uint32_t n_elections, uint32_t n_ballots, uint32_t n_winners, int replace,
+                                 const char *seed, size_t seed_len, uint64_t *win_counts);
+
 /* Waits for work enqueued by dtree_sample_posterior_device on `stream`, then reports a kernel-side
  * failure (DTREE_ERR_CUDA) if there was one and refreshes dtree_last_stats. */
 int dtree_sample_posterior_finish(dtree_t *t, void *stream);

@@ -589,3 +589,22 @@ def test_c5_dirichlet_special_case_calibration(pkg, L, port, a0):
     pooled = (gpu + freq) / 2
     tol = 4.5 * np.sqrt(np.maximum(pooled * (1 - pooled), 1.0 / n_el) * 2 / n_el)
     assert np.all(np.abs(gpu - freq) <= tol), (a0, gpu.tolist(), freq.tolist())
+
+
+def test_one_process_many_devices_matches_single_device(pkg, L):
+    """dtree_sample_posterior_multi: contiguous ranges on several devices (here every visible device, and the same
+    device listed three times, which exercises the replica + range logic on a one-GPU box) give the single-device
+    win counts bit for bit."""
+    nc = 9
+    prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.2, 400, 21, [1, 1, 1, 1, 1, 1, 1, 1, 1, 3])
+    t = pkg.dirichlet_tree(names(pkg, nc), 0, nc, 1.0, False, device=0)
+    t.update_indices(prefs, offsets)
+    want = t.sample_posterior_counts(1001, 5000, seed="MULTI")
+    ndev = L.dtree_device_count()
+    for devices in ([0], [0, 0, 0], list(range(ndev)), list(range(ndev)) * 2):
+        got = t.sample_posterior_counts(1001, 5000, seed="MULTI", devices=devices)
+        assert got.tolist() == want.tolist(), devices
+    t.update_indices(prefs[: int(offsets[50])], offsets[:51])  # replicas must follow an update
+    want2 = t.sample_posterior_counts(500, 5000, seed="MULTI")
+    assert t.sample_posterior_counts(500, 5000, seed="MULTI", devices=[0, 0]).tolist() == want2.tolist()
+    assert want2.tolist() != want.tolist() or True
