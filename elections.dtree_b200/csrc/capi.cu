@@ -99,6 +99,12 @@ double falling_factorial(uint32_t n, uint32_t k) {
 
 }  // namespace
 
+// Layout of dtree_last_stats (include/dtree_b200.h).
+enum OutStat {
+  kOutLaunches = 0, kOutElections, kOutEntries, kOutItems, kOutGammas, kOutBinomials, kOutRereads, kOutScratchBytes,
+  kOutH2D, kOutD2H, kOutSlots, kOutUrnItems, kOutMode, kOutArenaRuns, kOutCount = 16
+};
+
 struct dtree_ballots {
   std::vector<uint8_t> prefs;
   std::vector<uint64_t> offsets{0};
@@ -149,7 +155,7 @@ struct dtree {
   // callbacks, stats
   int (*should_abort)(void *) = nullptr;
   void *abort_user = nullptr;
-  uint64_t stats[16] = {0};
+  uint64_t stats[kOutCount] = {0};
 
   dtree(const HostParams &p, int dev) : tree(p), device(dev) {}
 };
@@ -213,7 +219,7 @@ int ensure_mirror(dtree *t, cudaStream_t s) {
   CUDA_TRY(t->d_obs_first.upload(t->h_obs_first, s));
   CUDA_TRY(t->d_obs_tally0.upload(t->h_obs_tally0, s));
   t->n_obs_entries = (uint32_t)F.obs_counts.size();
-  t->stats[8] += (F.node_base.size() + F.node_total.size() + F.slot_count.size() + F.slot_child.size()) * 4 +
+  t->stats[kOutH2D] += (F.node_base.size() + F.node_total.size() + F.slot_count.size() + F.slot_child.size()) * 4 +
                  F.slot_cand.size() + t->h_obs_keys.size() * 8 + F.obs_counts.size() * 5 + kMaxCandidates * 4;
   CUDA_TRY(cudaStreamSynchronize(s));  // pageable sources: the copies must not outlive a later update
   t->mirrored_version = t->tree.version();
@@ -367,6 +373,16 @@ int check_sampling_args(dtree *t, uint32_t n_ballots, const char *seed, size_t s
   return DTREE_OK;
 }
 
+void store_kernel_counters(dtree *t, const unsigned long long *st) {
+  t->stats[kOutEntries] = st[kStatEntries];
+  t->stats[kOutItems] = st[kStatItems];
+  t->stats[kOutGammas] = st[kStatGammas];
+  t->stats[kOutBinomials] = st[kStatBinomials];
+  t->stats[kOutRereads] = st[kStatRereads];
+  t->stats[kOutSlots] = st[kStatSlots];
+  t->stats[kOutUrnItems] = st[kStatUrnItems];
+}
+
 // Reads the deferred kernel's high-water marks and grows the cached sizing if an election came close.
 int absorb_usage(dtree *t) {
   if (!t->d_usage.p) return DTREE_OK;
@@ -378,7 +394,7 @@ int absorb_usage(dtree *t) {
     z.queue = std::max(z.queue, u[1]);
     z.big = std::max(z.big, u[2]);
   }
-  t->stats[13] = u[3];
+  t->stats[kOutArenaRuns] = u[3];
   return DTREE_OK;
 }
 
@@ -418,8 +434,8 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
 
   SimArgs a;
   memset(&a, 0, sizeof a);
-  auto fill_job = [&](SimArgs &a) {
-    fill_args(t, pl, a);
+  auto fill_job = [&](const Plan &plan, SimArgs &a) {
+    fill_args(t, plan, a);
     a.obs_key = t->d_obs_key.p;
     a.obs_cnt = t->d_obs_cnt.p;
     a.obs_first = t->d_obs_first.p;
@@ -459,10 +475,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
       pp.grid = (int)((pl.n_arenas + wpb - 1) / wpb);
       pilot_done = std::min<uint32_t>(n_elections, 4 * pl.n_arenas);
       SimArgs ap;
-      Plan saved = pl;
-      pl = pp;
-      fill_job(ap);
-      pl = saved;
+      fill_job(pp, ap);
       ap.scratch = t->d_arena.p;
       ap.scratch_stride = pl.arena_stride;
       ap.max_warps = pl.n_arenas;
@@ -495,7 +508,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     shape_deferred(t, n_elections - pilot_done, pl);
   }
   CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));
-  fill_job(a);
+  fill_job(pl, a);
   if (pl.deferred) {
     a.arena_scratch = t->d_arena.p;
     a.arena_stride = pl.arena_stride;
@@ -525,10 +538,10 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     CUDA_TRY(launch(pl, a, s));
     ++launches;
   }
-  t->stats[0] = launches;
-  t->stats[1] = n_elections;
-  t->stats[7] = pl.stride_block * pl.grid;
-  t->stats[12] = pl.deferred ? 1 : 0;
+  t->stats[kOutLaunches] = launches;
+  t->stats[kOutElections] = n_elections;
+  t->stats[kOutScratchBytes] = pl.stride_block * pl.grid;
+  t->stats[kOutMode] = pl.deferred ? 1 : 0;
   if (!sync_at_end) return DTREE_OK;
   CUDA_TRY(cudaStreamSynchronize(s));
   int err = 0;
@@ -536,20 +549,14 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   CUDA_TRY(cudaMemcpy(&err, t->d_error.p, sizeof err, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(st, t->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
   if (err) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
-  t->stats[2] = st[kStatEntries];
-  t->stats[3] = st[kStatItems];
-  t->stats[4] = st[kStatGammas];
-  t->stats[5] = st[kStatBinomials];
-  t->stats[6] = st[kStatRereads];
-  t->stats[10] = st[kStatSlots];
-  t->stats[11] = st[kStatUrnItems];
+  store_kernel_counters(t, st);
   if (pl.deferred) {
     rc = absorb_usage(t);
     if (rc) return rc;
   }
   if (h_orders) {
     CUDA_TRY(cudaMemcpy(h_orders, t->d_orders.p, (size_t)n_elections * nc, cudaMemcpyDeviceToHost));
-    t->stats[9] += (uint64_t)n_elections * nc;
+    t->stats[kOutD2H] += (uint64_t)n_elections * nc;
   }
   return DTREE_OK;
 }
@@ -606,7 +613,7 @@ int run_dump(dtree *t, uint64_t election, uint32_t n_sample, const char *seed, s
     CUDA_TRY(cudaMemcpy(cnt.data(), p_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(len.data(), p_len, (size_t)n, cudaMemcpyDeviceToHost));
   }
-  t->stats[9] += (uint64_t)n * (W * 8 + 5);
+  t->stats[kOutD2H] += (uint64_t)n * (W * 8 + 5);
   for (uint32_t i = 0; i < n; ++i) {
     for (uint32_t j = 0; j < len[i]; ++j) {
       uint64_t w = keys[(size_t)i * W + j / kPrefsPerWord];
@@ -822,7 +829,7 @@ int dtree_sample_posterior(dtree_t *t, uint64_t first_election, uint32_t n_elect
   if (rc) return rc;
   unsigned long long w[kMaxCandidates];
   CUDA_TRY(cudaMemcpy(w, t->d_wins.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  t->stats[9] += nc * 8;
+  t->stats[kOutD2H] += nc * 8;
   for (uint32_t c = 0; c < nc; ++c) win_counts[c] = w[c];
   return DTREE_OK;
 }
@@ -892,8 +899,8 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
     else if (rc == DTREE_OK)
       rc = rc2;
   }
-  t->stats[0] = used.size();
-  t->stats[1] = n_elections;
+  t->stats[kOutLaunches] = used.size();
+  t->stats[kOutElections] = n_elections;
   return rc;
 }
 
@@ -909,14 +916,8 @@ int dtree_sample_posterior_finish(dtree_t *t, void *stream) {
   CUDA_TRY(cudaMemcpy(&err, t->d_error.p, sizeof err, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(st, t->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
   if (err) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
-  t->stats[2] = st[kStatEntries];
-  t->stats[3] = st[kStatItems];
-  t->stats[4] = st[kStatGammas];
-  t->stats[5] = st[kStatBinomials];
-  t->stats[6] = st[kStatRereads];
-  t->stats[10] = st[kStatSlots];
-  t->stats[11] = st[kStatUrnItems];
-  if (t->stats[12] == 1) return absorb_usage(t);
+  store_kernel_counters(t, st);
+  if (t->stats[kOutMode] == 1) return absorb_usage(t);
   return DTREE_OK;
 }
 
@@ -1066,7 +1067,7 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
 
 int dtree_last_stats(const dtree_t *t, uint64_t *out, uint32_t cap) {
   if (!t || !out) return fail(DTREE_ERR_ARG, "null argument");
-  for (uint32_t i = 0; i < cap && i < 16; ++i) out[i] = t->stats[i];
+  for (uint32_t i = 0; i < cap && i < (uint32_t)kOutCount; ++i) out[i] = t->stats[i];
   return DTREE_OK;
 }
 
