@@ -233,3 +233,34 @@ def test_rcpp_shim_compiles_against_the_c_abi():
                         os.path.join(root, "elections.dtree_b200", "host", "r", "R_tree_b200.cpp")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_update_property_random_ballot_streams(pkg, port):
+    """Property test (hypothesis): any stream of valid ballots — blank, partial, full, repeated, in any batching —
+    leaves the host tree with exactly the reference's nodes, slot order and counts (irv_node.cpp:176-221)."""
+    from hypothesis import given, settings, strategies as st
+
+    @st.composite
+    def streams(draw):
+        nc = draw(st.integers(2, 9))
+        ballot = st.lists(st.integers(0, nc - 1), unique=True, max_size=nc)
+        batches = draw(st.lists(st.lists(ballot, max_size=12), min_size=1, max_size=4))
+        return nc, draw(st.integers(0, nc)), batches
+
+    @settings(max_examples=60, deadline=None)
+    @given(streams())
+    def check(args):
+        nc, mx, batches = args
+        t = pkg.dirichlet_tree(pkg.workloads.candidate_names(nc), 0, mx, 1.0, False)
+        o = port.tree(nc, 0, mx, 1.0, False)
+        for batch in batches:
+            if not batch:
+                continue
+            prefs, offsets = oracle.ballots_to_csr(batch)
+            t.update_indices(prefs, offsets)
+            o.update((prefs, offsets))
+        assert oracle.parse_node_dump(t.export_nodes()) == oracle.parse_node_dump(o.dump_nodes())
+        assert t.n_observed == o.n_observed()
+        o.close()
+
+    check()

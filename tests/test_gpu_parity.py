@@ -428,7 +428,7 @@ def test_vd_prior_is_uniform_over_ballot_types(pkg, L):
     assert np.all(np.abs(x / n_el - n * p) < 5 * np.sqrt(var_one / n_el))
 
 
-@pytest.mark.parametrize("cfg", ["C1", "C2small", "C5a", "C5b", "replace"])
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C2small", "C5a", "C5b", "replace"])
 def test_posterior_win_probabilities_match_the_oracle(pkg, L, port, cfg):
     """Posterior win probabilities, GPU vs oracle, within 4.5 sigma of the binomial Monte-Carlo error of the
     difference. C1 is BASELINE config 1 in full."""
@@ -438,6 +438,11 @@ def test_posterior_win_probabilities_match_the_oracle(pkg, L, port, cfg):
         nc, mn, mx, a0, vd = c["n_candidates"], c["min_depth"], c["max_depth"], c["a0"], c["vd"]
         prefs, offsets = W.observed_ballots("C1")
         n_el, n_b, replace = c["n_elections"] * 4, c["n_ballots"], False
+    elif cfg == "C2":  # BASELINE config 2 in full: 6 candidates, Wakehurst-shaped partial ballots, 50 k ballots, 10 k elections
+        c = W.CONFIGS["C2"]
+        nc, mn, mx, a0, vd = c["n_candidates"], c["min_depth"], c["max_depth"], c["a0"], c["vd"]
+        prefs, offsets = W.observed_ballots("C2")
+        n_el, n_b, replace = c["n_elections"], c["n_ballots"], False
     elif cfg == "C2small":
         nc, mn, mx, a0, vd = 6, 0, 5, 1.0, False
         prefs, offsets = W.wakehurst_sample(300, 2)
