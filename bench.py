@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--urn-max", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-mode", action="store_true", help="do not also time the other kernel")
-    ap.add_argument("--mode", type=int, default=-1, choices=[-1, 0, 1],
+    ap.add_argument("--mode", type=int, default=-1, choices=[-1, 0, 1, 2],
                     help="1: deferred expansion kernel, 0: materialising kernel, -1: the library's choice")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -254,7 +254,7 @@ def main():
         return {"value": n_el * world * steps / (ms / 1e3), "elapsed_ms": ms, "steps": steps, "elections_per_gpu": n_el,
                 "kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in kernel_ev])),
                 "kernel_ms_steps": [round(a.elapsed_time(b), 2) for a, b in kernel_ev], "stats": st,
-                "kernel": "deferred_kernel" if st["mode"] == 1 else "simulate_kernel"}
+                "kernel": {0: "simulate_kernel", 1: "deferred_kernel", 2: "lane_kernel"}[st["mode"]]}
 
     sampler = ClockSampler(local) if rank == 0 else None
     main = measure(args.mode, epg, args.steps, args.warmup, 0)
@@ -263,7 +263,7 @@ def main():
     # the other kernel on the same inputs (fewer elections when it is the slower, materialising one)
     other = None
     if not args.single_mode:
-        om = 0 if stats["mode"] == 1 else 1
+        om = 0 if stats["mode"] >= 1 else 1
         o_epg = max(296, epg // 8) if om == 0 else epg
         other = measure(om, o_epg, max(2, min(args.steps, 3)), 3, 1 << 40)
     t.tune(mode=args.mode)

@@ -136,7 +136,7 @@ struct dtree {
   DevBuf<uint8_t> d_orders;
   // deferred kernel: worst-case overflow arenas, their locks, usage high-water marks [3] + arena runs [1]
   DevBuf<uint8_t> d_arena;
-  DevBuf<unsigned int> d_locks, d_usage;
+  DevBuf<unsigned int> d_locks, d_usage, d_retry;  // d_retry: [0] count, [4..] election indices
   struct Sizing {
     bool valid = false;
     uint64_t version = 0;
@@ -144,7 +144,8 @@ struct dtree {
     double a0 = 0;
     bool vd = false, use_obs = false;
     uint32_t pool = 0, queue = 0, big = 0;              // largest usage seen (items)
-    uint32_t cap_pool = 0, cap_queue = 0, cap_big = 0;  // capacities in force
+    uint32_t cap_pool = 0, cap_queue = 0, cap_big = 0;  // capacities in force (warp per election)
+    uint32_t lane_pool = 0, lane_queue = 0, lane_big = 0;  // capacities in force (thread per election)
   } sizing;
   // tuning
   int block_threads = 0, blocks_per_sm = 0;
@@ -235,6 +236,7 @@ struct Plan {
   uint64_t stride;        // scratch bytes per block (materialising kernel) or per warp (deferred kernel)
   uint64_t stride_block;  // scratch bytes per block
   bool deferred = false;
+  bool lane = false;  // deferred algorithm, one thread per election (lane_kernel)
 };
 
 template <int W>
@@ -360,6 +362,7 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
 
 cudaError_t launch(const Plan &pl, const SimArgs &a, cudaStream_t s) {
   LaunchCfg cfg{pl.block, pl.log_gamma, pl.grid, s};
+  if (pl.lane) return launch_lane(a, cfg);
   if (pl.deferred) return launch_deferred(a, cfg);
   return pl.W == 1 ? launch_simulate<1>(a, cfg) : pl.W == 2 ? launch_simulate<2>(a, cfg) : launch_simulate<3>(a, cfg);
 }
@@ -414,7 +417,8 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   const bool use_obs = !replace;
   const uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->tree.n_observed();
   Plan pl;
-  pl.deferred = t->mode == 1;
+  pl.deferred = t->mode == 1 || t->mode == 2;
+  bool want_lane = t->mode == 2;
   if (t->mode < 0) pl.deferred = true;  // the deferred kernel is the faster one on every configuration measured
   if (pl.deferred) {
     rc = make_plan_deferred(t, n_sample, n_elections, pl);
@@ -451,6 +455,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
 
   uint32_t pilot_done = 0;
   uint64_t launches = 0;
+  Plan pp;  // pilot / replay launches of deferred_kernel in the worst-case arenas
   if (pl.deferred) {
     const HostParams &P = t->tree.P;
     dtree::Sizing &z = t->sizing;
@@ -466,7 +471,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     if (!hit) {
       // Pilot: a few elections run directly in the worst-case arenas (they cannot overflow and their
       // results count); their high-water marks size everybody else's arena.
-      Plan pp = pl;
+      pp = pl;
       pp.cap_items = pl.arena_items;
       pp.cap_queue = pl.arena_queue;
       pp.cap_big = pl.arena_big;
@@ -505,7 +510,49 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     pl.cap_items = std::min(z.cap_pool, pl.arena_items);
     pl.cap_queue = std::min(z.cap_queue, pl.arena_queue);
     pl.cap_big = std::min(z.cap_big, pl.arena_big);
-    shape_deferred(t, n_elections - pilot_done, pl);
+    // One thread per election (lane_kernel): 32x more arenas in flight, so a tighter margin (2x the largest election
+    // seen, revised only when an election has used more than 80 % of it); an election that still outgrows its arena
+    // is replayed by deferred_kernel in a worst-case arena.
+    if (!hit || 5ull * z.pool > 4ull * z.lane_pool) z.lane_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 2ull * z.pool + 512);
+    if (!hit || 5ull * z.queue > 4ull * z.lane_queue) z.lane_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 2ull * z.queue + 512);
+    if (!hit || 5ull * z.big > 4ull * z.lane_big) z.lane_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 2ull * z.big + 64);
+    Plan lp = pl;
+    lp.lane = true;
+    lp.block = 128;
+    lp.cap_items = std::min(z.lane_pool, pl.arena_items);
+    lp.cap_queue = std::min(z.lane_queue, pl.arena_queue);
+    lp.cap_big = std::min(z.lane_big, pl.arena_big);
+    lp.stride = (deferred_scratch_bytes(lp.cap_items, lp.cap_queue, lp.cap_big) + 255) & ~255ull;  // per thread
+    lp.stride_block = lp.stride * lp.block;
+    {
+      int occ = lane_blocks_per_sm(pl.log_gamma);
+      if (occ <= 0) return fail(DTREE_ERR_CUDA, "lane kernel cannot be resident");
+      if (t->blocks_per_sm > 0) occ = std::min(occ, t->blocks_per_sm);
+      const uint64_t resident = (uint64_t)occ * t->sm_count;
+      const uint64_t fit = std::max<uint64_t>(1, pl.mem_budget / lp.stride_block);
+      const uint64_t need = ((uint64_t)(n_elections - pilot_done) + lp.block - 1) / lp.block;
+      lp.grid = (int)std::max<uint64_t>(1, std::min(std::min(resident, fit), need));
+      if (t->mode < 0) {
+        // Automatic choice: a thread per election pays off when there are enough elections to fill the machine
+        // (a thread runs its election alone, start to finish) and memory lets most of the threads be resident.
+        const uint64_t lane_threads = std::min(resident, fit) * lp.block;
+        const uint64_t warp_elections = (uint64_t)pl.blocks_per_sm * t->sm_count * (pl.block / 32);
+        want_lane = lane_threads >= 16 * warp_elections && (uint64_t)(n_elections - pilot_done) * 10 >= lane_threads * 7;
+      }
+    }
+    if (want_lane) {
+      pp = pl;  // the replay launch: deferred_kernel, one warp per worst-case arena
+      pp.cap_items = pl.arena_items;
+      pp.cap_queue = pl.arena_queue;
+      pp.cap_big = pl.arena_big;
+      pp.stride = pl.arena_stride;
+      pp.block = 128;
+      pp.grid = (int)((pl.n_arenas + 3) / 4);
+      pl = lp;
+      CUDA_TRY(t->d_retry.reserve((1u << 20) + 4));
+    } else {
+      shape_deferred(t, n_elections - pilot_done, pl);
+    }
   }
   CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));
   fill_job(pl, a);
@@ -522,9 +569,27 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     a.max_warps = 0xFFFFFFFFu;
   }
 
-  // One launch per wave. Without an abort callback the whole range is one wave.
+  SimArgs ar;  // lane mode: the replay of overflowed elections, enqueued right behind every wave
+  if (pl.lane) {
+    a.retry_list = t->d_retry.p + 4;
+    a.retry_count = t->d_retry.p;
+    a.retry_cap = 1u << 20;
+    a.n_arenas = 0;
+    fill_job(pp, ar);
+    ar.scratch = t->d_arena.p;
+    ar.scratch_stride = pl.arena_stride;
+    ar.max_warps = pl.n_arenas;
+    ar.n_arenas = 0;
+    ar.usage = t->d_usage.p;
+    ar.arena_runs = t->d_usage.p + 3;
+    ar.election_list = t->d_retry.p + 4;
+    ar.n_elections_ptr = t->d_retry.p;
+  }
+  // One launch per wave. Without an abort callback the whole range is one wave (lane mode: at most 2^20
+  // elections per wave, the capacity of its replay list).
   uint32_t wave = n_elections;
-  if (t->should_abort) wave = (uint32_t)std::min<uint64_t>(n_elections, (uint64_t)pl.grid * (pl.deferred ? 4096 : 64));
+  if (t->should_abort) wave = (uint32_t)std::min<uint64_t>(n_elections, (uint64_t)pl.grid * (pl.lane ? 1024 : pl.deferred ? 4096 : 64));
+  if (pl.lane) wave = std::min<uint32_t>(wave, 1u << 20);
   for (uint32_t done = pilot_done; done < n_elections; done += wave) {
     uint32_t n = std::min(wave, n_elections - done);
     if (t->should_abort && done > pilot_done) {
@@ -535,13 +600,25 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     a.n_elections = n;
     a.elim_orders = h_orders ? t->d_orders.p + (size_t)done * nc : nullptr;
     CUDA_TRY(cudaMemsetAsync(t->d_counter.p, 0, sizeof(unsigned int), s));
+    if (pl.lane) CUDA_TRY(cudaMemsetAsync(t->d_retry.p, 0, sizeof(unsigned int), s));
     CUDA_TRY(launch(pl, a, s));
     ++launches;
+    if (pl.lane) {
+      ar.first_election = a.first_election;
+      ar.n_elections = std::min<uint32_t>(n, 1u << 20);
+      ar.elim_orders = a.elim_orders;
+      CUDA_TRY(cudaMemsetAsync(t->d_counter.p, 0, sizeof(unsigned int), s));
+      Plan replay = pp;
+      replay.deferred = true;
+      replay.lane = false;
+      CUDA_TRY(launch(replay, ar, s));
+      ++launches;
+    }
   }
   t->stats[kOutLaunches] = launches;
   t->stats[kOutElections] = n_elections;
   t->stats[kOutScratchBytes] = pl.stride_block * pl.grid;
-  t->stats[kOutMode] = pl.deferred ? 1 : 0;
+  t->stats[kOutMode] = pl.lane ? 2 : pl.deferred ? 1 : 0;
   if (!sync_at_end) return DTREE_OK;
   CUDA_TRY(cudaStreamSynchronize(s));
   int err = 0;
@@ -680,7 +757,7 @@ int dtree_destroy(dtree_t *t) {
     t->d_slot_child.release(); t->d_slot_cand.release(); t->d_obs_first.release(); t->d_obs_key.release();
     t->d_scratch.release(); t->d_wins.release(); t->d_stats.release(); t->d_counter.release(); t->d_error.release();
     t->d_entry_count.release(); t->d_orders.release();
-    t->d_arena.release(); t->d_locks.release(); t->d_usage.release();
+    t->d_arena.release(); t->d_locks.release(); t->d_usage.release(); t->d_retry.release();
   }
   delete t;
   return DTREE_OK;
@@ -917,7 +994,7 @@ int dtree_sample_posterior_finish(dtree_t *t, void *stream) {
   CUDA_TRY(cudaMemcpy(st, t->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
   if (err) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
   store_kernel_counters(t, st);
-  if (t->stats[kOutMode] == 1) return absorb_usage(t);
+  if (t->stats[kOutMode] >= 1) return absorb_usage(t);
   return DTREE_OK;
 }
 
@@ -1056,7 +1133,8 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   if (!strcmp(key, "block_threads")) t->block_threads = (int)value;
   else if (!strcmp(key, "blocks_per_sm")) t->blocks_per_sm = (int)value;
   else if (!strcmp(key, "mode")) {
-    if (value < -1 || value > 1) return fail(DTREE_ERR_ARG, "mode must be -1 (auto), 0 (materialise) or 1 (deferred)");
+    if (value < -1 || value > 2)
+      return fail(DTREE_ERR_ARG, "mode must be -1 (auto), 0 (materialise), 1 (deferred, warp per election) or 2 (deferred, thread per election)");
     t->mode = (int)value;
   } else if (!strcmp(key, "urn_max")) {
     if (value < 0 || value > 8) return fail(DTREE_ERR_ARG, "urn_max must be in [0, 8]");

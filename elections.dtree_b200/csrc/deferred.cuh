@@ -400,12 +400,14 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) deferred_kernel(const __gr
   __syncthreads();
   const uint32_t n_rounds = a.elim_orders ? nc - 1 : nc - a.n_winners;
 
+  const uint32_t n_total = a.n_elections_ptr ? min(*a.n_elections_ptr, a.n_elections) : a.n_elections;
   for (;;) {
     if (gwarp >= a.max_warps) break;
     uint32_t e = 0;
     if (lane == 0) e = atomicAdd(a.work_counter, 1u);
     e = __shfl_sync(0xffffffffu, e, 0);
-    if (e >= a.n_elections) break;
+    if (e >= n_total) break;
+    if (a.election_list) e = a.election_list[e];
     const RngKey key = election_key(a.seed, a.first_election + e);
     uint32_t eliminated = 0, my_order = 0xFFu, tie_rounds = 0;
     // First in the warp's own arena; if that proves too small, once more in a worst-case arena.

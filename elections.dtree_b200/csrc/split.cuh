@@ -60,6 +60,12 @@ struct SimArgs {
   unsigned int *arena_runs;    // number of elections re-run in an arena
   uint32_t *usage;             // [3] high-water marks: parked pool, work queue, big list
   uint32_t max_warps;          // warps with a larger grid-wide index stay idle (pilot launches)
+  // replaying a list of elections (lane_kernel's overflow list): indices relative to first_election
+  const uint32_t *election_list;   // NULL: elections 0..n_elections-1
+  const uint32_t *n_elections_ptr; // NULL, or device count that caps n_elections (known only on the device)
+  uint32_t *retry_list;            // lane_kernel: elections whose arena overflowed
+  unsigned int *retry_count;
+  uint32_t retry_cap;
   // outputs
   unsigned long long *win_counts;  // [nc], added to
   uint8_t *elim_orders;            // NULL or [n_elections * nc]

@@ -172,10 +172,11 @@ void dtree_ballots_free(dtree_ballots_t *b);
 int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user);
 
 /* ---- tuning / introspection (not part of the reference interface) ----------------------------
- * key: "mode" — how dtree_sample_posterior* simulates an election: 1 expands a tree node only when IRV
- *        needs to look below it; 0 materialises every sampled ballot first, as the reference does
- *        (dirichlet_tree.h:216-235 then irv_ballot.cpp:42-138); -1 (default) picks 1 unless its worst-case
- *        scratch does not fit the device. Both give bit-identical outcomes;
+ * key: "mode" — how dtree_sample_posterior* simulates an election: 1 and 2 expand a tree node only when IRV
+ *        needs to look below it, with a warp (1) or a single thread (2) per election; 0 materialises every
+ *        sampled ballot first, as the reference does (dirichlet_tree.h:216-235 then irv_ballot.cpp:42-138);
+ *        -1 (default) picks 2 when there are enough elections to fill the GPU with one per thread, else 1,
+ *        and 0 only if the worst-case scratch of 1/2 does not fit the device. All give bit-identical outcomes;
  *      "block_threads" (0 = auto), "blocks_per_sm" (0 = auto), "urn_max" (largest count split by the
  *        Polya-urn shortcut instead of Gamma variates, <= 8).
  * Returns DTREE_ERR_ARG for an unknown key. */

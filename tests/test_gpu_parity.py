@@ -253,7 +253,7 @@ def test_determinism_and_range_splitting(pkg, L):
         acc += ww
         parts.append(oo)
     assert acc.tolist() == w.tolist() and np.array_equal(np.vstack(parts), orders)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         for bt in (32, 64, 128, 256):  # neither the kernel nor its launch shape may matter
             t.tune(block_threads=bt, mode=mode)
             w2, o2 = t.sample_posterior_counts(300, 2000, seed="SPLIT", return_orders=True)
@@ -270,8 +270,9 @@ def test_determinism_and_range_splitting(pkg, L):
     (32, 0, 32, 1.0, False, 300, 5000, False), (14, 3, 9, 2.0, True, 200, 3000, True),
     (2, 0, 2, 1.0, False, 20, 100, False), (3, 0, 2, 0.5, False, 30, 90, False), (3, 1, 3, 1.0, True, 0, 7, False)])
 def test_deferred_equals_materialised(pkg, L, nc, mn, mx, a0, vd, n_obs, n_ballots, replace):
-    """mode=1 (expand a node only when IRV looks below it) and mode=0 (materialise every ballot, as the
-    reference does) must give the same elimination order for every election and the same win counts:
+    """mode=1 / mode=2 (expand a node only when IRV looks below it; a warp / a thread per election) and mode=0
+    (materialise every ballot, as the reference does) must give the same elimination order for every election and
+    the same win counts:
     both evaluate the same counter-based draws. Includes observed ballots longer than max_depth, n_ballots
     == n_observed (nothing sampled), an empty tree, a0 = 0 and every key width."""
     pmf = np.ones(nc + 1)
@@ -282,23 +283,24 @@ def test_deferred_equals_materialised(pkg, L, nc, mn, mx, a0, vd, n_obs, n_ballo
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             t.update_indices(prefs, offsets)
-    res = []
-    for mode in (0, 1):
+    res = {}
+    for mode in (0, 1, 2):
         t.tune(mode=mode)
+        out = []
         for nw in ((1, 2) if nc > 2 else (1,)):
-            res.append((mode, nw) + t.sample_posterior_counts(400, n_ballots, n_winners=nw, replace=replace,
-                                                              seed="DEFER", return_orders=True))
-            res.append((mode, nw, t.sample_posterior_counts(400, n_ballots, n_winners=nw, replace=replace,
-                                                            seed="DEFER"), None))
+            out.append(t.sample_posterior_counts(400, n_ballots, n_winners=nw, replace=replace, seed="DEFER",
+                                                 return_orders=True))
+            out.append((t.sample_posterior_counts(400, n_ballots, n_winners=nw, replace=replace, seed="DEFER"), None))
         assert t.last_stats()["mode"] == mode
-    half = len(res) // 2
-    for a, b in zip(res[:half], res[half:]):
-        assert a[1] == b[1] and a[2].tolist() == b[2].tolist()
-        assert (a[3] is None and b[3] is None) or np.array_equal(a[3], b[3])
-    assert res[0][2].tolist() == res[1][2].tolist()  # with and without the order output
+        res[mode] = out
+    for mode in (1, 2):
+        for a, b in zip(res[0], res[mode]):
+            assert a[0].tolist() == b[0].tolist(), mode
+            assert (a[1] is None and b[1] is None) or np.array_equal(a[1], b[1]), mode
+    assert res[0][0][0].tolist() == res[0][1][0].tolist()  # with and without the order output
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("nc,mn,mx,a0,vd,n_obs,n_ballots,replace", [
     (4, 0, 3, 1.0, False, 1000, 10_000, False), (6, 0, 5, 1.0, False, 300, 3000, False),
     (8, 7, 7, 0.01, True, 200, 5000, False), (10, 0, 10, 1.0, False, 2000, 20_000, False),
@@ -567,13 +569,14 @@ def test_full_size_configs_conserve_ballots_and_agree_across_kernels(pkg, L, nam
     assert len(set(sampled)) == len(sampled) and all(len(set(b)) == len(b) for b in sampled[:20000])
     n_el = {"C2": 3000, "C3": 400, "C4": 60}[name]
     res = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         t.tune(mode=mode)
         res[mode] = t.sample_posterior_counts(n_el, cfg["n_ballots"], seed="FULL", return_orders=True)
         assert int(res[mode][0].sum()) == n_el
         plain = t.sample_posterior_counts(n_el, cfg["n_ballots"], seed="FULL")  # with the early-stop short-cuts
         assert plain.tolist() == res[mode][0].tolist()
-    assert res[0][0].tolist() == res[1][0].tolist() and np.array_equal(res[0][1], res[1][1])
+    for mode in (1, 2):
+        assert res[0][0].tolist() == res[mode][0].tolist() and np.array_equal(res[0][1], res[mode][1]), mode
     # the order reported for election 5 is one the reference rule allows on election 5's ballots
     ok, _ = oracle.load("port").irv_check_order((p, off), cnt, nc, res[1][1][5].astype(np.uint32))
     assert ok

@@ -14,7 +14,7 @@ W = pkg.workloads
 N_EL = {"C1": 200_000, "C2": 40_000, "C3": 1200, "C4": 300, "C5": 4000}
 names = [x for x in sys.argv[1:] if x.startswith("C")] or ["C1", "C2", "C3", "C4", "C5"]
 MODE = int(os.environ.get("DTREE_MODE", "1"))
-if MODE == 1:
+if MODE >= 1:
     N_EL = {k: (v * 10 if k != "C4" else v) for k, v in N_EL.items()}
 shapes = [(0, 0, 8)] + [(b, 0, 8) for b in (32, 64, 128, 256)] + [(0, 0, 0), (0, 0, 2), (0, 0, 4)]
 for name in names:
@@ -27,7 +27,7 @@ for name in names:
     t_update = time.perf_counter() - t0
     n = N_EL[name]
     for block, bps, urn in shapes:
-        if MODE == 1 and block == 32:
+        if MODE >= 1 and block == 32:
             continue
         t.tune(block_threads=block, blocks_per_sm=bps, urn_max=urn, mode=MODE)
         try:
