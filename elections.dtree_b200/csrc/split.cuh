@@ -109,8 +109,15 @@ __device__ __forceinline__ void warp_tally_add(uint32_t *s_tally, bool valid, ui
 
 // i-th (0-based) candidate not in `used`, ascending.
 __device__ __forceinline__ uint32_t nth_unused(uint32_t used, uint32_t nc, uint32_t i) {
-  const uint32_t avail = ~used & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
-  return __fns(avail, 0u, (int)i + 1);
+  uint32_t v = ~used & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+  // branch-free select of the i-th set bit by halving (the __fns intrinsic is a slow software loop)
+  uint32_t r = 0, c;
+  c = (uint32_t)__popc(v & 0xFFFFu); if (i >= c) { r += 16u; i -= c; v >>= 16; }
+  c = (uint32_t)__popc(v & 0xFFu);   if (i >= c) { r += 8u;  i -= c; v >>= 8; }
+  c = (uint32_t)__popc(v & 0xFu);    if (i >= c) { r += 4u;  i -= c; v >>= 4; }
+  c = (uint32_t)__popc(v & 0x3u);    if (i >= c) { r += 2u;  i -= c; v >>= 2; }
+  c = v & 1u;                        if (i >= c) { r += 1u; }
+  return r;
 }
 
 // First standing preference of a ballot: scans from the front, skipping eliminated candidates.
