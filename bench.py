@@ -279,7 +279,9 @@ def main():
     h2d0 = t.last_stats()["h2d_bytes"]
     barrier()
     t0 = time.perf_counter()
+    e2e_ms = []
     for i in range(e2e_steps):
+        ts = time.perf_counter()
         N.check(L.dtree_invalidate_device(t._h))
         first = ((args.warmup + args.steps + i) * world + rank) * epg
         w = t.sample_posterior_counts(epg, cfg["n_ballots"], seed=SEED, first_election=first)
@@ -287,6 +289,7 @@ def main():
             wt = torch.from_numpy(w.astype(np.int64)).to(dev)
             dist.all_reduce(wt, op=dist.ReduceOp.SUM)
             w = wt.cpu().numpy()
+        e2e_ms.append(round((time.perf_counter() - ts) * 1e3, 2))
     barrier()
     e2e_s = time.perf_counter() - t0
     e2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -295,7 +298,7 @@ def main():
     e2e_s = float(e2.item())
     h2d = (t.last_stats()["h2d_bytes"] - h2d0) // e2e_steps
     e2e = {"value": epg * world * e2e_steps / e2e_s, "unit": "elections/s", "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(nc * 8), "steps": e2e_steps}
+           "d2h_bytes_per_step": int(nc * 8), "steps": e2e_steps, "ms_steps": e2e_ms}
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:

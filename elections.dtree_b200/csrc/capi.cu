@@ -510,12 +510,12 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     pl.cap_items = std::min(z.cap_pool, pl.arena_items);
     pl.cap_queue = std::min(z.cap_queue, pl.arena_queue);
     pl.cap_big = std::min(z.cap_big, pl.arena_big);
-    // One thread per election (lane_kernel): 32x more arenas in flight, so a tighter margin (2x the largest election
-    // seen, revised only when an election has used more than 80 % of it); an election that still outgrows its arena
+    // One thread per election (lane_kernel): 32x more arenas in flight, so a tighter margin (3x the largest election
+    // seen, revised only when an election has used more than 75 % of it); an election that still outgrows its arena
     // is replayed by deferred_kernel in a worst-case arena.
-    if (!hit || 5ull * z.pool > 4ull * z.lane_pool) z.lane_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 2ull * z.pool + 512);
-    if (!hit || 5ull * z.queue > 4ull * z.lane_queue) z.lane_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 2ull * z.queue + 512);
-    if (!hit || 5ull * z.big > 4ull * z.lane_big) z.lane_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 2ull * z.big + 64);
+    if (!hit || 4ull * z.pool > 3ull * z.lane_pool) z.lane_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 3ull * z.pool + 512);
+    if (!hit || 4ull * z.queue > 3ull * z.lane_queue) z.lane_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 3ull * z.queue + 512);
+    if (!hit || 4ull * z.big > 3ull * z.lane_big) z.lane_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 3ull * z.big + 64);
     Plan lp = pl;
     lp.lane = true;
     lp.block = 128;

@@ -221,7 +221,7 @@ __device__ void lane_split_big(const SimArgs &a, LaneShared<BLOCK> &sh, const De
 }
 
 template <int BLOCK, bool LOG>
-__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) lane_kernel(const __grid_constant__ SimArgs a) {
+__global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_constant__ SimArgs a) {
   __shared__ LaneShared<BLOCK> sh;
   __shared__ uint32_t s_wins[kMaxCandidates];
   const int tid = threadIdx.x, lane = tid & 31;
