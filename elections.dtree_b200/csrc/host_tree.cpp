@@ -109,76 +109,83 @@ void FlatTree::node_prefix(uint32_t node, std::vector<uint8_t> &out) const {
 }
 
 // Breadth-first renumbering: nodes of one depth contiguous, siblings adjacent, so that a
-// frontier processed in order reads slot_count with unit stride.
+// frontier processed in order reads slot_count with unit stride. One pass over a queue of arena
+// ids; every output array is sized up front (the CSR has exactly as many slots as the arena).
 void HostTree::flatten(FlatTree &F) const {
   const uint32_t nc = P.nc;
+  const size_t n = depth_.size(), total_slots = counts_.size();
   F = FlatTree();
-  struct QItem { int32_t arena; uint32_t parent_slot; uint8_t path[kMaxCandidates]; };
-  std::vector<QItem> cur(1), next;
-  cur[0].arena = 0;
-  cur[0].parent_slot = UINT32_MAX;
-  for (uint32_t i = 0; i < nc; ++i) cur[0].path[i] = (uint8_t)i;
-  F.node_base.push_back(0);
-  std::vector<uint8_t> prefix;
-  uint32_t depth = 0;
-  while (!cur.empty()) {
-    F.level_first.push_back(F.n_nodes());
-    next.clear();
-    uint32_t K = nc - depth;
-    // ids of this level's children are assigned in order of appearance
-    uint32_t next_id = F.n_nodes() + (uint32_t)cur.size();
-    for (const QItem &q : cur) {
-      uint64_t base = base_[q.arena];
-      uint32_t fbase = (uint32_t)F.slot_count.size();
-      for (uint32_t j = 0; j <= K; ++j) {
-        F.slot_count.push_back(counts_[base + j]);
-        F.slot_cand.push_back(j < K ? q.path[depth + j] : (uint8_t)0xFF);
-        int32_t c = j < K ? child_[base + j] : -1;
-        if (c >= 0) {
-          QItem nq;
-          nq.arena = c;
-          nq.parent_slot = fbase + j;
-          std::memcpy(nq.path, q.path, nc);
-          std::swap(nq.path[depth], nq.path[depth + j]);
-          next.push_back(nq);
-          F.slot_child.push_back((int32_t)next_id++);
-        } else {
-          F.slot_child.push_back(-1);
-        }
-      }
-      uint32_t child_total = 0;
-      for (uint32_t j = 0; j < K; ++j) child_total += counts_[base + j];
-      F.node_total.push_back(child_total);
-      F.node_depth.push_back((uint8_t)depth);
-      F.node_parent_slot.push_back(q.parent_slot);
-      F.node_base.push_back((uint32_t)F.slot_count.size());
-      // Observed ballots that END at this node: the stop slot, and at K == 2 (never expanded,
-      // irv_node.cpp:210) also the two child slots, which stand for prefix+cand (with or
-      // without the implied last preference).
-      uint32_t stop = counts_[base + K];
-      bool leafish = (K == 2);
-      if (stop || (leafish && (counts_[base] || counts_[base + 1]))) {
-        prefix.assign(q.path, q.path + depth);
-        if (stop) {
-          F.obs_prefs.insert(F.obs_prefs.end(), prefix.begin(), prefix.end());
-          F.obs_offsets.push_back(F.obs_prefs.size());
-          F.obs_counts.push_back(stop);
-        }
-        if (leafish)
-          for (uint32_t j = 0; j < 2; ++j)
-            if (counts_[base + j]) {
-              F.obs_prefs.insert(F.obs_prefs.end(), prefix.begin(), prefix.end());
-              F.obs_prefs.push_back(q.path[depth + j]);
-              F.obs_offsets.push_back(F.obs_prefs.size());
-              F.obs_counts.push_back(counts_[base + j]);
-            }
+  F.node_base.resize(n + 1);
+  F.node_total.resize(n);
+  F.node_depth.resize(n);
+  F.node_parent_slot.resize(n);
+  F.slot_count.resize(total_slots);
+  F.slot_child.resize(total_slots);
+  F.slot_cand.resize(total_slots);
+  F.obs_offsets.push_back(0);
+  std::vector<int32_t> order(n);      // flat id -> arena id, filled as children are discovered
+  std::vector<uint8_t> paths(n * nc);  // candidate permutation of every node (irv_node.cpp:219 swaps)
+  order[0] = 0;
+  for (uint32_t i = 0; i < nc; ++i) paths[i] = (uint8_t)i;
+  F.node_parent_slot[0] = UINT32_MAX;
+  size_t head = 0, tail = 1;
+  uint32_t fbase = 0, cur_depth = UINT32_MAX;
+  while (head < tail) {
+    const size_t i = head++;
+    const int32_t arena = order[i];
+    const uint32_t depth = depth_[arena], K = nc - depth;
+    const uint64_t base = base_[arena];
+    const uint8_t *p = &paths[i * nc];
+    if (depth != cur_depth) {
+      F.level_first.push_back((uint32_t)i);
+      cur_depth = depth;
+    }
+    F.node_base[i] = fbase;
+    F.node_depth[i] = (uint8_t)depth;
+    uint32_t child_total = 0;
+    for (uint32_t j = 0; j < K; ++j) {
+      const uint32_t cnt = counts_[base + j];
+      child_total += cnt;
+      F.slot_count[fbase + j] = cnt;
+      F.slot_cand[fbase + j] = p[depth + j];
+      const int32_t c = child_[base + j];
+      if (c >= 0) {
+        const size_t id = tail++;
+        order[id] = c;
+        uint8_t *q = &paths[id * nc];
+        std::memcpy(q, p, nc);
+        std::swap(q[depth], q[depth + j]);
+        F.node_parent_slot[id] = fbase + j;
+        F.slot_child[fbase + j] = (int32_t)id;
+      } else {
+        F.slot_child[fbase + j] = -1;
       }
     }
-    cur.swap(next);
-    ++depth;
+    const uint32_t stop = counts_[base + K];
+    F.slot_count[fbase + K] = stop;
+    F.slot_cand[fbase + K] = 0xFF;
+    F.slot_child[fbase + K] = -1;
+    F.node_total[i] = child_total;
+    // Observed ballots that END at this node: the stop slot, and at K == 2 (never expanded,
+    // irv_node.cpp:210) also the two child slots, which stand for prefix+cand (with or
+    // without the implied last preference).
+    if (stop) {
+      F.obs_prefs.insert(F.obs_prefs.end(), p, p + depth);
+      F.obs_offsets.push_back(F.obs_prefs.size());
+      F.obs_counts.push_back(stop);
+    }
+    if (K == 2)
+      for (uint32_t j = 0; j < 2; ++j)
+        if (counts_[base + j]) {
+          F.obs_prefs.insert(F.obs_prefs.end(), p, p + depth);
+          F.obs_prefs.push_back(p[depth + j]);
+          F.obs_offsets.push_back(F.obs_prefs.size());
+          F.obs_counts.push_back(counts_[base + j]);
+        }
+    fbase += K + 1;
   }
-  F.level_first.push_back(F.n_nodes());
-  F.obs_offsets.insert(F.obs_offsets.begin(), 0);
+  F.node_base[n] = fbase;
+  F.level_first.push_back((uint32_t)n);
 }
 
 // FNV-1a over the seed bytes, then a splitmix64 finaliser: same string => same 64-bit key,
