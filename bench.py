@@ -276,6 +276,9 @@ def main():
 
     # ---- e2e: host buffers through the C ABI, mirror invalidated so that the tree upload is inside -------------
     e2e_steps = max(1, min(args.steps, 3))
+    for i in range(2):  # untimed warm-up of this path too (it lets the library settle its scratch sizing)
+        N.check(L.dtree_invalidate_device(t._h))
+        t.sample_posterior_counts(epg, cfg["n_ballots"], seed=SEED, first_election=(1 << 41) + (i * world + rank) * epg)
     h2d0 = t.last_stats()["h2d_bytes"]
     barrier()
     t0 = time.perf_counter()
