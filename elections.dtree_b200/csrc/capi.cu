@@ -142,10 +142,11 @@ struct dtree {
     uint64_t version = 0;
     uint32_t n_sample = 0, urn_max = 0, min_depth = 0, max_depth = 0;
     double a0 = 0;
-    bool vd = false, use_obs = false;
+    bool vd = false, use_obs = false, short_cuts = false;  // short_cuts: IRV may stop early (smaller elections)
     uint32_t pool = 0, queue = 0, big = 0;              // largest usage seen (items)
     uint32_t cap_pool = 0, cap_queue = 0, cap_big = 0;  // capacities in force (warp per election)
     uint32_t lane_pool = 0, lane_queue = 0, lane_big = 0;  // capacities in force (thread per election)
+    double nodes_per_election = 0;                          // node splits per election, last measured
   } sizing;
   // tuning
   int block_threads = 0, blocks_per_sm = 0;
@@ -398,6 +399,8 @@ int absorb_usage(dtree *t) {
     z.big = std::max(z.big, u[2]);
   }
   t->stats[kOutArenaRuns] = u[3];
+  if (z.valid && t->stats[kOutElections] > 0 && t->stats[kOutItems] > 0)
+    z.nodes_per_election = (double)t->stats[kOutItems] / (double)t->stats[kOutElections];
   return DTREE_OK;
 }
 
@@ -461,7 +464,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     dtree::Sizing &z = t->sizing;
     const bool hit = z.valid && z.version == t->tree.version() && z.n_sample == n_sample && z.urn_max == t->urn_max &&
                      z.min_depth == P.min_depth && z.max_depth == P.max_depth && z.a0 == P.a0 && z.vd == P.vd &&
-                     z.use_obs == use_obs;
+                     z.use_obs == use_obs && z.short_cuts == (n_winners == 1 && h_orders == nullptr);
     CUDA_TRY(t->d_arena.reserve(pl.arena_stride * pl.n_arenas));
     // Arena locks start free at every call: a launch that died must not leave one held.
     CUDA_TRY(t->d_locks.reserve(kMaxArenas));
@@ -499,8 +502,11 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
       z.valid = true;
       z.version = t->tree.version();
       z.n_sample = n_sample; z.urn_max = t->urn_max; z.min_depth = P.min_depth; z.max_depth = P.max_depth;
-      z.a0 = P.a0; z.vd = P.vd; z.use_obs = use_obs;
+      z.a0 = P.a0; z.vd = P.vd; z.use_obs = use_obs; z.short_cuts = n_winners == 1 && h_orders == nullptr;
       z.pool = u[0]; z.queue = u[1]; z.big = u[2];
+      unsigned long long st[kStatCount];
+      CUDA_TRY(cudaMemcpy(st, t->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
+      z.nodes_per_election = (double)st[kStatItems] / std::max<uint32_t>(pilot_done, 1);
     }
     // Capacities get a 4x margin over the largest election seen and are only revised when an election has
     // used more than half of them (so that a new maximum does not reallocate the scratch every time).
@@ -537,7 +543,10 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
         // (a thread runs its election alone, start to finish) and memory lets most of the threads be resident.
         const uint64_t lane_threads = std::min(resident, fit) * lp.block;
         const uint64_t warp_elections = (uint64_t)pl.blocks_per_sm * t->sm_count * (pl.block / 32);
-        want_lane = lane_threads >= 16 * warp_elections && (uint64_t)(n_elections - pilot_done) * 10 >= lane_threads * 7;
+        // ... and the elections are light: a heavy election (a close race expands tens of thousands of nodes) is
+        // better served by the 32 lanes and shared-memory tile of deferred_kernel than by one thread.
+        want_lane = lane_threads >= 16 * warp_elections && (uint64_t)(n_elections - pilot_done) * 10 >= lane_threads * 7 &&
+                    z.nodes_per_election <= 5000.0;
       }
     }
     if (want_lane) {
