@@ -616,3 +616,32 @@ def test_one_process_many_devices_matches_single_device(pkg, L):
     want2 = t.sample_posterior_counts(500, 5000, seed="MULTI")
     assert t.sample_posterior_counts(500, 5000, seed="MULTI", devices=[0, 0]).tolist() == want2.tolist()
     assert want2.tolist() != want.tolist() or True
+
+
+def test_handles_release_their_device_memory(pkg, L):
+    """Create / sample / destroy in a loop (all three kernels, dumps, replicas): device memory in use must come back
+    to where it started (RDirichletTree's finaliser path, R_tree.cpp:63-66)."""
+    import gc
+    import torch
+    W = pkg.workloads
+    prefs, offsets = W.plackett_luce_ballots(8, 0.3, 300, 4, None)
+
+    def cycle():
+        t = pkg.dirichlet_tree(names(pkg, 8), 0, 8, 1.0, False, device=0)
+        t.update_indices(prefs, offsets)
+        for mode in (0, 1, 2):
+            t.tune(mode=mode)
+            t.sample_posterior_counts(2000, 3000, seed="leak")
+        t.sample_posterior_counts(500, 3000, seed="leak", devices=[0, 0])
+        t.sample_predictive(1000, seed="leak")
+        del t
+        gc.collect()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    for _ in range(5):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < 64 << 20, (free0, free1)
