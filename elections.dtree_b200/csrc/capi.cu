@@ -311,14 +311,18 @@ int make_plan_deferred(dtree *t, uint32_t n_sample, uint32_t n_elections, Plan &
   if (occ <= 0) return fail(DTREE_ERR_CUDA, "deferred kernel cannot be resident (%s)", cudaGetErrorString(cudaGetLastError()));
   if (t->blocks_per_sm > 0) occ = std::min(occ, t->blocks_per_sm);
   pl.blocks_per_sm = occ;
+  // ... and there are never more live nodes than distinct prefixes
+  double prefixes = 0;
+  for (uint32_t l = 0; l < P.nc; ++l) prefixes += falling_factorial(P.nc, l);
   uint64_t worst = (uint64_t)n_sample + t->tree.n_nodes() + 64;
+  if (prefixes + 64 < (double)worst) worst = (uint64_t)prefixes + 64;
   if (worst > 0x7FFFFFF0ull) {
     pl.n_arenas = 0;
     return DTREE_OK;  // caller falls back to the materialising kernel
   }
   pl.arena_items = (uint32_t)worst;
   pl.arena_queue = (uint32_t)worst;
-  pl.arena_big = (uint32_t)((uint64_t)n_sample / (t->urn_max + 1) + 64);
+  pl.arena_big = (uint32_t)std::min<uint64_t>((uint64_t)n_sample / (t->urn_max + 1) + 64, worst);
   pl.arena_stride = (deferred_scratch_bytes(pl.arena_items, pl.arena_queue, pl.arena_big) + 255) & ~255ull;
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));

@@ -645,3 +645,25 @@ def test_handles_release_their_device_memory(pkg, L):
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info(0)
     assert free0 - free1 < 64 << 20, (free0, free1)
+
+
+def test_largest_ballot_counts(pkg, L, port):
+    """n_ballots near the top of the reference's `unsigned` range (4 x 10^9 per election): counts stay exact
+    (f64 binomial rejection, u32 tallies), the three kernels agree, and win probabilities match the oracle
+    (5 sigma of the binomial Monte-Carlo error)."""
+    nc, n_b, n_el = 4, 4_000_000_000, 3000
+    prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.02, 50, 2, [1, 1, 1, 1, 2])
+    t, o = make_pair(pkg, port, nc, 0, nc, 1.0, False, prefs, offsets)
+    p, off, cnt = t.posterior_set_indices(1, n_b, False, "BIG")
+    assert int(cnt.astype(np.int64).sum()) == n_b
+    res = []
+    for mode in (0, 1, 2):
+        t.tune(mode=mode)
+        res.append(t.sample_posterior_counts(n_el, n_b, seed="BIG"))
+        assert t.last_stats()["mode"] == mode
+    assert res[0].tolist() == res[1].tolist() == res[2].tolist()
+    gpu = res[0] / float(n_el)
+    freq, _ = o.sample_posterior(n_el, n_b, 1, False, 4, "BIG")
+    pooled = (gpu + freq) / 2
+    tol = 5 * np.sqrt(np.maximum(pooled * (1 - pooled), 1.0 / n_el) * 2 / n_el)
+    assert np.all(np.abs(gpu - freq) <= tol), (gpu.tolist(), freq.tolist())
