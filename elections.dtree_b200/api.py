@@ -164,8 +164,25 @@ class dirichlet_tree:
         buf = (C.c_uint64 * 16)()
         N.check(self._L.dtree_last_stats(self._h, buf, 16))
         keys = ["launches", "elections", "entries", "items", "gammas", "binomial_attempts", "irv_rereads",
-                "scratch_bytes", "h2d_bytes", "d2h_bytes", "slots", "urn_items", "mode", "arena_runs"]
+                "scratch_bytes", "h2d_bytes", "d2h_bytes", "slots", "urn_items", "mode", "arena_runs", "build_launches"]
         return {k: int(buf[i]) for i, k in enumerate(keys)}
+
+    _IMAGE_ARRAYS = {"node_base": (0, "uint32"), "node_total": (1, "uint32"), "slot_count": (2, "uint32"),
+                     "slot_child": (3, "int32"), "slot_cand": (4, "uint8"), "obs_key": (5, "uint64"),
+                     "obs_cnt": (6, "uint32"), "obs_first": (7, "uint8"), "obs_tally0": (8, "uint32")}
+
+    def device_image(self):
+        """The device mirror of the tree, copied back array by array (test hook, dtree_b200_debug.h)."""
+        import numpy as np
+        out = {}
+        for name, (which, dt) in self._IMAGE_ARRAYS.items():
+            need = C.c_uint64(0)
+            N.check(self._L.dtree_debug_device_image(self._h, which, None, 0, C.byref(need)))
+            a = np.zeros(need.value // np.dtype(dt).itemsize, dtype=dt)
+            if a.size:
+                N.check(self._L.dtree_debug_device_image(self._h, which, a.ctypes.data_as(C.c_void_p), a.nbytes, C.byref(need)))
+            out[name] = a
+        return out
 
     # ---- ballots ------------------------------------------------------------------------------------
     def _to_indices(self, ballots):

@@ -15,6 +15,7 @@
 #include "dtree_b200_debug.h"
 #include "host_tree.h"
 #include "launch.h"
+#include "tree_build.h"
 
 using namespace dtb;
 
@@ -37,32 +38,6 @@ int fail(int code, const char *fmt, ...) {
     cudaError_t e_ = (expr);                                                                    \
     if (e_ != cudaSuccess) return fail(DTREE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
   } while (0)
-
-template <typename T>
-struct DevBuf {
-  T *p = nullptr;
-  size_t n = 0;  // elements allocated
-  cudaError_t reserve(size_t want) {
-    if (want <= n && p) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-    if (want == 0) want = 1;
-    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
-    if (e == cudaSuccess) n = want;
-    return e;
-  }
-  cudaError_t upload(const std::vector<T> &v, cudaStream_t s) {
-    cudaError_t e = reserve(v.size());
-    if (e != cudaSuccess || v.empty()) return e;
-    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-  }
-};
 
 struct DeviceGuard {
   int prev = -1;
@@ -102,7 +77,7 @@ double falling_factorial(uint32_t n, uint32_t k) {
 // Layout of dtree_last_stats (include/dtree_b200.h).
 enum OutStat {
   kOutLaunches = 0, kOutElections, kOutEntries, kOutItems, kOutGammas, kOutBinomials, kOutRereads, kOutScratchBytes,
-  kOutH2D, kOutD2H, kOutSlots, kOutUrnItems, kOutMode, kOutArenaRuns, kOutCount = 16
+  kOutH2D, kOutD2H, kOutSlots, kOutUrnItems, kOutMode, kOutArenaRuns, kOutBuildLaunches, kOutCount = 16
 };
 
 struct dtree_ballots {
@@ -112,7 +87,15 @@ struct dtree_ballots {
 };
 
 struct dtree {
-  HostTree tree;
+  // Observed ballots as given to dtree_update (validated): the device builds the tree from this log
+  // (tree_build.cu); the host trie below is brought up to date only for the host-side exports.
+  std::vector<uint8_t> log_prefs;
+  std::vector<uint64_t> log_offsets{0};
+  uint64_t n_observed = 0, depth_mask = 0, version = 0;  // version: bumped by update/reset
+  HostTree tree;              // parameters (tree.P) + lazily synchronised trie
+  uint64_t trie_ballots = 0;  // log entries already inserted into `tree`
+  uint64_t n_nodes = 1;       // of the current mirror
+  bool host_build = false;    // tuning "host_build": mirror = HostTree::flatten + upload (measurement aid)
   int device;
   int sm_count = 0;
   size_t smem_optin = 0;
@@ -122,11 +105,7 @@ struct dtree {
   std::vector<uint64_t> h_obs_keys;
   std::vector<uint8_t> h_obs_first;
   std::vector<uint32_t> h_obs_tally0;
-  DevBuf<uint32_t> d_node_base, d_node_total, d_slot_count, d_obs_cnt, d_obs_tally0;
-  DevBuf<int32_t> d_slot_child;
-  DevBuf<uint8_t> d_slot_cand, d_obs_first;
-  DevBuf<uint64_t> d_obs_key;
-  uint32_t n_obs_entries = 0;
+  DeviceTreeStore dev;  // tree arrays, packed observed ballots, ballot log (tree_build.h)
   // scratch + small device state
   DevBuf<uint8_t> d_scratch;
   DevBuf<unsigned long long> d_wins, d_stats;
@@ -181,10 +160,18 @@ DeviceParams device_params(const HostParams &P) {
   return D;
 }
 
-// Host image of the device mirror: the CSR arrays plus the packed observed entries. Rebuilt only when the
-// tree changes; dtree_invalidate_device drops the device copy but keeps this, so re-mirroring is a plain upload.
+// Brings the host trie up to date with the ballot log.
+void sync_trie(dtree *t) {
+  const uint64_t n = t->log_offsets.size() - 1;
+  if (t->trie_ballots < n) t->tree.insert_ballots(t->log_prefs.data(), t->log_offsets.data(), t->trie_ballots, n);
+  t->trie_ballots = n;
+}
+
+// Host image of the tree: the CSR arrays plus the packed observed entries, for the host-side exports
+// and the "host_build" mirror. Rebuilt only when the tree changes.
 int ensure_host_image(dtree *t) {
-  if (t->image_version == t->tree.version()) return DTREE_OK;
+  if (t->image_version == t->version) return DTREE_OK;
+  sync_trie(t);
   t->tree.flatten(t->flat);
   const FlatTree &F = t->flat;
   const uint32_t nc = t->tree.P.nc;
@@ -202,29 +189,47 @@ int ensure_host_image(dtree *t) {
     t->h_obs_first[i] = len ? F.obs_prefs[F.obs_offsets[i]] : 0xFF;
     if (len) t->h_obs_tally0[t->h_obs_first[i]] += F.obs_counts[i];
   }
-  t->image_version = t->tree.version();
+  t->image_version = t->version;
   return DTREE_OK;
 }
 
+// The device mirror. Product path: the tree is built on the device from the ballot log. With the
+// tuning "host_build" the host trie is flattened and uploaded instead (kept to measure against).
 int ensure_mirror(dtree *t, cudaStream_t s) {
-  if (t->mirrored_version == t->tree.version()) return DTREE_OK;
+  if (t->mirrored_version == t->version) return DTREE_OK;
+  if (!t->host_build) {
+    BuildStats bs;
+    bool too_big = false;
+    CUDA_TRY(build_tree_on_device(t->dev, t->tree.P.nc, t->log_prefs.data(), t->log_offsets.data(),
+                                  t->log_offsets.size() - 1, s, &bs, &too_big));
+    if (too_big) return fail(DTREE_ERR_STATE, "tree has too many outcome slots for 32-bit indices");
+    t->stats[kOutH2D] += bs.h2d_bytes;
+    t->stats[kOutBuildLaunches] = bs.launches;
+    t->n_nodes = t->dev.n_nodes;
+    t->mirrored_version = t->version;
+    return DTREE_OK;
+  }
   int rc = ensure_host_image(t);
   if (rc) return rc;
   const FlatTree &F = t->flat;
-  CUDA_TRY(t->d_node_base.upload(F.node_base, s));
-  CUDA_TRY(t->d_node_total.upload(F.node_total, s));
-  CUDA_TRY(t->d_slot_count.upload(F.slot_count, s));
-  CUDA_TRY(t->d_slot_child.upload(F.slot_child, s));
-  CUDA_TRY(t->d_slot_cand.upload(F.slot_cand, s));
-  CUDA_TRY(t->d_obs_key.upload(t->h_obs_keys, s));
-  CUDA_TRY(t->d_obs_cnt.upload(F.obs_counts, s));
-  CUDA_TRY(t->d_obs_first.upload(t->h_obs_first, s));
-  CUDA_TRY(t->d_obs_tally0.upload(t->h_obs_tally0, s));
-  t->n_obs_entries = (uint32_t)F.obs_counts.size();
+  CUDA_TRY(t->dev.node_base.upload(F.node_base, s));
+  CUDA_TRY(t->dev.node_total.upload(F.node_total, s));
+  CUDA_TRY(t->dev.slot_count.upload(F.slot_count, s));
+  CUDA_TRY(t->dev.slot_child.upload(F.slot_child, s));
+  CUDA_TRY(t->dev.slot_cand.upload(F.slot_cand, s));
+  CUDA_TRY(t->dev.obs_key.upload(t->h_obs_keys, s));
+  CUDA_TRY(t->dev.obs_cnt.upload(F.obs_counts, s));
+  CUDA_TRY(t->dev.obs_first.upload(t->h_obs_first, s));
+  CUDA_TRY(t->dev.obs_tally0.upload(t->h_obs_tally0, s));
+  t->dev.n_obs = (uint32_t)F.obs_counts.size();
+  t->dev.n_nodes = F.n_nodes();
+  t->dev.n_slots = (uint32_t)F.slot_count.size();
+  t->dev.log_ballots = t->dev.log_bytes = 0;  // the device log is not maintained on this path
+  t->n_nodes = F.n_nodes();
   t->stats[kOutH2D] += (F.node_base.size() + F.node_total.size() + F.slot_count.size() + F.slot_child.size()) * 4 +
                  F.slot_cand.size() + t->h_obs_keys.size() * 8 + F.obs_counts.size() * 5 + kMaxCandidates * 4;
   CUDA_TRY(cudaStreamSynchronize(s));  // pageable sources: the copies must not outlive a later update
-  t->mirrored_version = t->tree.version();
+  t->mirrored_version = t->version;
   return DTREE_OK;
 }
 
@@ -259,7 +264,7 @@ int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, P
   entries = std::min<double>((double)n_sample, entries);
   pl.cap_items = (uint32_t)std::max(items, 1.0);
   pl.cap_entries = (uint32_t)std::max(entries, 1.0);
-  uint32_t nobs = use_obs ? t->n_obs_entries : 0;
+  uint32_t nobs = use_obs ? t->dev.n_obs : 0;
   pl.stride = pl.W == 1 ? scratch_bytes<1>(pl.cap_items, pl.cap_entries, nobs)
             : pl.W == 2 ? scratch_bytes<2>(pl.cap_items, pl.cap_entries, nobs)
                         : scratch_bytes<3>(pl.cap_items, pl.cap_entries, nobs);
@@ -269,7 +274,7 @@ int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, P
   int block = t->block_threads;
   if (block == 0) {
     // A block works on one election; size it to the widest frontier it is likely to see.
-    double work = std::min<double>(items, 1.0 + (double)t->tree.n_nodes() + (double)n_sample / 8);
+    double work = std::min<double>(items, 1.0 + (double)t->n_nodes + (double)n_sample / 8);
     block = work <= 48 ? 32 : work <= 512 ? 64 : work <= 8192 ? 128 : 256;
   }
   bool okb = false;
@@ -314,7 +319,7 @@ int make_plan_deferred(dtree *t, uint32_t n_sample, uint32_t n_elections, Plan &
   // ... and there are never more live nodes than distinct prefixes
   double prefixes = 0;
   for (uint32_t l = 0; l < P.nc; ++l) prefixes += falling_factorial(P.nc, l);
-  uint64_t worst = (uint64_t)n_sample + t->tree.n_nodes() + 64;
+  uint64_t worst = (uint64_t)n_sample + t->n_nodes + 64;
   if (prefixes + 64 < (double)worst) worst = (uint64_t)prefixes + 64;
   if (worst > 0x7FFFFFF0ull) {
     pl.n_arenas = 0;
@@ -347,12 +352,12 @@ void shape_deferred(dtree *t, uint32_t n_elections, Plan &pl) {
 void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
   memset(&a, 0, sizeof a);
   a.P = device_params(t->tree.P);
-  a.T.node_base = t->d_node_base.p;
-  a.T.node_total = t->d_node_total.p;
-  a.T.slot_count = t->d_slot_count.p;
-  a.T.slot_child = t->d_slot_child.p;
-  a.T.slot_cand = t->d_slot_cand.p;
-  a.T.n_nodes = t->flat.n_nodes();
+  a.T.node_base = t->dev.node_base.p;
+  a.T.node_total = t->dev.node_total.p;
+  a.T.slot_count = t->dev.slot_count.p;
+  a.T.slot_child = t->dev.slot_child.p;
+  a.T.slot_cand = t->dev.slot_cand.p;
+  a.T.n_nodes = (uint32_t)t->n_nodes;
   a.urn_max = t->urn_max;
   a.scratch = t->d_scratch.p;
   a.scratch_stride = pl.stride;
@@ -415,14 +420,14 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   int rc = check_sampling_args(t, n_ballots, seed, seed_len);
   if (rc) return rc;
   const uint32_t nc = t->tree.P.nc;
-  if ((uint64_t)n_ballots < t->tree.n_observed())  // R_tree.cpp:183-186
+  if ((uint64_t)n_ballots < t->n_observed)  // R_tree.cpp:183-186
     return fail(DTREE_ERR_STATE, "`nBallots` must be larger than the number of ballots observed to obtain the posterior.");
   if (n_winners < 1 || n_winners >= nc) return fail(DTREE_ERR_ARG, "n_winners must be in [1, n_candidates)");
   if (n_elections == 0) return DTREE_OK;
   rc = ensure_mirror(t, s);
   if (rc) return rc;
   const bool use_obs = !replace;
-  const uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->tree.n_observed();
+  const uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->n_observed;
   Plan pl;
   pl.deferred = t->mode == 1 || t->mode == 2;
   bool want_lane = t->mode == 2;
@@ -447,11 +452,11 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   memset(&a, 0, sizeof a);
   auto fill_job = [&](const Plan &plan, SimArgs &a) {
     fill_args(t, plan, a);
-    a.obs_key = t->d_obs_key.p;
-    a.obs_cnt = t->d_obs_cnt.p;
-    a.obs_first = t->d_obs_first.p;
-    a.obs_tally0 = t->d_obs_tally0.p;
-    a.n_obs = use_obs ? t->n_obs_entries : 0;
+    a.obs_key = t->dev.obs_key.p;
+    a.obs_cnt = t->dev.obs_cnt.p;
+    a.obs_first = t->dev.obs_first.p;
+    a.obs_tally0 = t->dev.obs_tally0.p;
+    a.n_obs = use_obs ? t->dev.n_obs : 0;
     a.use_obs = use_obs ? 1 : 0;
     a.seed = hash_seed(seed, seed_len);
     a.n_sample = n_sample;
@@ -466,7 +471,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   if (pl.deferred) {
     const HostParams &P = t->tree.P;
     dtree::Sizing &z = t->sizing;
-    const bool hit = z.valid && z.version == t->tree.version() && z.n_sample == n_sample && z.urn_max == t->urn_max &&
+    const bool hit = z.valid && z.version == t->version && z.n_sample == n_sample && z.urn_max == t->urn_max &&
                      z.min_depth == P.min_depth && z.max_depth == P.max_depth && z.a0 == P.a0 && z.vd == P.vd &&
                      z.use_obs == use_obs && z.short_cuts == (n_winners == 1 && h_orders == nullptr);
     CUDA_TRY(t->d_arena.reserve(pl.arena_stride * pl.n_arenas));
@@ -504,7 +509,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
       unsigned int u[4];
       CUDA_TRY(cudaMemcpy(u, t->d_usage.p, sizeof u, cudaMemcpyDeviceToHost));
       z.valid = true;
-      z.version = t->tree.version();
+      z.version = t->version;
       z.n_sample = n_sample; z.urn_max = t->urn_max; z.min_depth = P.min_depth; z.max_depth = P.max_depth;
       z.a0 = P.a0; z.vd = P.vd; z.use_obs = use_obs; z.short_cuts = n_winners == 1 && h_orders == nullptr;
       z.pool = u[0]; z.queue = u[1]; z.big = u[2];
@@ -766,8 +771,7 @@ int dtree_destroy(dtree_t *t) {
   t->replicas.clear();
   if (t->sm_count) {
     DeviceGuard g(t->device);
-    t->d_node_base.release(); t->d_node_total.release(); t->d_slot_count.release(); t->d_obs_cnt.release(); t->d_obs_tally0.release();
-    t->d_slot_child.release(); t->d_slot_cand.release(); t->d_obs_first.release(); t->d_obs_key.release();
+    t->dev.release_all();
     t->d_scratch.release(); t->d_wins.release(); t->d_stats.release(); t->d_counter.release(); t->d_error.release();
     t->d_entry_count.release(); t->d_orders.release();
     t->d_arena.release(); t->d_locks.release(); t->d_usage.release(); t->d_retry.release();
@@ -815,24 +819,43 @@ int dtree_update(dtree_t *t, const uint8_t *prefs, const uint64_t *offsets, uint
   if (n_short) *n_short = 0;
   if (n == 0) return DTREE_OK;
   if (!offsets || (!prefs && offsets[n] > 0)) return fail(DTREE_ERR_ARG, "null ballot buffers");
-  if (t->tree.n_observed() + n > 0xFFFFFFFFull) return fail(DTREE_ERR_STATE, "more than 2^32-1 observed ballots");
+  if (t->n_observed + n > 0xFFFFFFFFull) return fail(DTREE_ERR_STATE, "more than 2^32-1 observed ballots");
   std::string err;
-  if (!t->tree.update(prefs, offsets, n, n_short, err)) return fail(DTREE_ERR_ARG, "%s", err.c_str());
+  uint64_t mask = 0;
+  if (!t->tree.P.validate(prefs, offsets, n, n_short, &mask, err)) return fail(DTREE_ERR_ARG, "%s", err.c_str());
+  // append to the log, offsets rebased onto it
+  const uint64_t at = t->log_prefs.size(), first = offsets[0];
+  t->log_prefs.insert(t->log_prefs.end(), prefs + first, prefs + offsets[n]);
+  t->log_offsets.reserve(t->log_offsets.size() + n);
+  for (uint64_t i = 1; i <= n; ++i) t->log_offsets.push_back(at + (offsets[i] - first));
+  t->n_observed += n;  // R_tree.cpp:149
+  t->depth_mask |= mask;
+  ++t->version;
   return DTREE_OK;
 }
 
 int dtree_reset(dtree_t *t) {
   if (!t) return fail(DTREE_ERR_ARG, "null handle");
+  t->log_prefs.clear();
+  t->log_offsets.assign(1, 0);
+  t->n_observed = t->depth_mask = 0;
   t->tree.reset();
+  t->trie_ballots = 0;
+  t->dev.log_ballots = t->dev.log_bytes = 0;
+  ++t->version;
   return DTREE_OK;
 }
-uint64_t dtree_n_observed(const dtree_t *t) { return t->tree.n_observed(); }
-uint64_t dtree_observed_depth_mask(const dtree_t *t) { return t->tree.depth_mask(); }
-uint64_t dtree_n_nodes(const dtree_t *t) { return t->tree.n_nodes(); }
+uint64_t dtree_n_observed(const dtree_t *t) { return t->n_observed; }
+uint64_t dtree_observed_depth_mask(const dtree_t *t) { return t->depth_mask; }
+uint64_t dtree_n_nodes(const dtree_t *t) {
+  sync_trie(const_cast<dtree_t *>(t));
+  return t->tree.n_nodes();
+}
 
 int dtree_export_nodes(const dtree_t *t, uint32_t *buf, uint64_t cap, uint64_t *needed) {
   if (!t || !needed) return fail(DTREE_ERR_ARG, "null argument");
   FlatTree F;
+  sync_trie(const_cast<dtree_t *>(t));
   t->tree.flatten(F);
   const uint32_t nc = t->tree.P.nc;
   std::vector<uint32_t> out;
@@ -863,6 +886,7 @@ int dtree_export_nodes(const dtree_t *t, uint32_t *buf, uint64_t cap, uint64_t *
 int dtree_observed(const dtree_t *t, dtree_ballots_t **out) {
   if (!t || !out) return fail(DTREE_ERR_ARG, "null argument");
   FlatTree F;
+  sync_trie(const_cast<dtree_t *>(t));
   t->tree.flatten(F);
   dtree_ballots *b = new dtree_ballots;
   append_observed(F, b);
@@ -899,6 +923,7 @@ int dtree_sync_device(dtree_t *t) {
 int dtree_invalidate_device(dtree_t *t) {
   if (!t) return fail(DTREE_ERR_ARG, "null handle");
   t->mirrored_version = ~0ull;
+  t->dev.log_ballots = t->dev.log_bytes = 0;  // the next mirror starts from host memory again
   return DTREE_OK;
 }
 
@@ -959,8 +984,18 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
       r = nullptr;
     }
     if (!r) r = new dtree(t->tree.P, dev);
-    if (r->tree.version() != t->tree.version() || r->tree.n_observed() != t->tree.n_observed()) r->tree = t->tree;
+    if (r->version != t->version || r->n_observed != t->n_observed) {  // same ballot log, own mirror
+      r->log_prefs = t->log_prefs;
+      r->log_offsets = t->log_offsets;
+      r->n_observed = t->n_observed;
+      r->depth_mask = t->depth_mask;
+      r->version = t->version;
+      r->tree.reset();
+      r->trie_ballots = 0;
+      r->dev.log_ballots = r->dev.log_bytes = 0;
+    }
     r->tree.P = t->tree.P;
+    r->host_build = t->host_build;
     r->mode = t->mode;
     r->urn_max = t->urn_max;
     r->block_threads = t->block_threads;
@@ -1036,15 +1071,16 @@ int dtree_posterior_set(dtree_t *t, uint64_t election, uint32_t n_ballots, int r
   *out = nullptr;
   int rc = check_sampling_args(t, n_ballots, seed, seed_len);
   if (rc) return rc;
-  if (!replace && (uint64_t)n_ballots < t->tree.n_observed())
+  if (!replace && (uint64_t)n_ballots < t->n_observed)
     return fail(DTREE_ERR_STATE, "`nBallots` must be larger than the number of ballots observed to obtain the posterior.");
   rc = bind_device(t);
   if (rc) return rc;
   DeviceGuard g(t->device);
   if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
   dtree_ballots *b = new dtree_ballots;
-  uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->tree.n_observed();
+  uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->n_observed;
   rc = ensure_mirror(t, 0);
+  if (!rc && !replace) rc = ensure_host_image(t);
   if (!rc && !replace) append_observed(t->flat, b);
   if (!rc && n_sample) rc = run_dump(t, election, n_sample, seed, seed_len, b);
   if (rc) {
@@ -1152,7 +1188,39 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   } else if (!strcmp(key, "urn_max")) {
     if (value < 0 || value > 8) return fail(DTREE_ERR_ARG, "urn_max must be in [0, 8]");
     t->urn_max = (uint32_t)value;
+  } else if (!strcmp(key, "host_build")) {
+    t->host_build = value != 0;
+    t->mirrored_version = ~0ull;
   } else return fail(DTREE_ERR_ARG, "unknown tuning key '%s'", key);
+  return DTREE_OK;
+}
+
+int dtree_debug_device_image(dtree_t *t, int which, void *out, uint64_t cap_bytes, uint64_t *needed_bytes) {
+  if (!t || !needed_bytes) return fail(DTREE_ERR_ARG, "null argument");
+  int rc = bind_device(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  rc = ensure_mirror(t, 0);
+  if (rc) return rc;
+  const DeviceTreeStore &S = t->dev;
+  const int W = key_words_for(t->tree.P.nc);
+  const void *src = nullptr;
+  uint64_t bytes = 0;
+  switch (which) {
+    case 0: src = S.node_base.p; bytes = ((uint64_t)S.n_nodes + 1) * 4; break;
+    case 1: src = S.node_total.p; bytes = (uint64_t)S.n_nodes * 4; break;
+    case 2: src = S.slot_count.p; bytes = (uint64_t)S.n_slots * 4; break;
+    case 3: src = S.slot_child.p; bytes = (uint64_t)S.n_slots * 4; break;
+    case 4: src = S.slot_cand.p; bytes = S.n_slots; break;
+    case 5: src = S.obs_key.p; bytes = (uint64_t)S.n_obs * W * 8; break;
+    case 6: src = S.obs_cnt.p; bytes = (uint64_t)S.n_obs * 4; break;
+    case 7: src = S.obs_first.p; bytes = S.n_obs; break;
+    case 8: src = S.obs_tally0.p; bytes = kMaxCandidates * 4; break;
+    default: return fail(DTREE_ERR_ARG, "unknown device array %d", which);
+  }
+  *needed_bytes = bytes;
+  if (out && cap_bytes >= bytes && bytes) CUDA_TRY(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
   return DTREE_OK;
 }
 

@@ -26,10 +26,7 @@ void HostTree::reset() {
   base_.clear();
   counts_.clear();
   child_.clear();
-  n_observed_ = 0;
-  depth_mask_ = 0;
   new_node(0);
-  ++version_;
 }
 
 int32_t HostTree::new_node(uint32_t depth) {
@@ -69,9 +66,10 @@ void HostTree::insert(const uint8_t *b, uint32_t len) {
   }
 }
 
-bool HostTree::update(const uint8_t *prefs, const uint64_t *offsets, uint64_t n, uint64_t *n_short,
-                      std::string &err) {
-  uint64_t shorts = 0;
+bool HostParams::validate(const uint8_t *prefs, const uint64_t *offsets, uint64_t n, uint64_t *n_short,
+                          uint64_t *depth_mask, std::string &err) const {
+  const HostParams &P = *this;
+  uint64_t shorts = 0, mask = 0;
   for (uint64_t i = 0; i < n; ++i) {
     if (offsets[i + 1] < offsets[i]) { err = "ballot offsets must be non-decreasing"; return false; }
     uint64_t len = offsets[i + 1] - offsets[i];
@@ -84,16 +82,15 @@ bool HostTree::update(const uint8_t *prefs, const uint64_t *offsets, uint64_t n,
       seen |= 1u << c;
     }
     if (len > 0 && len < P.min_depth) ++shorts;  // R_tree.cpp:139
-  }
-  for (uint64_t i = 0; i < n; ++i) {
-    uint32_t len = (uint32_t)(offsets[i + 1] - offsets[i]);
-    insert(prefs + offsets[i], len);
-    n_observed_ += 1;            // R_tree.cpp:149
-    depth_mask_ |= 1ull << len;  // R_tree.cpp:151
+    mask |= 1ull << len;                          // R_tree.cpp:151
   }
   if (n_short) *n_short = shorts;
-  if (n) ++version_;
+  if (depth_mask) *depth_mask = mask;
   return true;
+}
+
+void HostTree::insert_ballots(const uint8_t *prefs, const uint64_t *offsets, uint64_t first, uint64_t n) {
+  for (uint64_t i = first; i < n; ++i) insert(prefs + offsets[i], (uint32_t)(offsets[i + 1] - offsets[i]));
 }
 
 void FlatTree::node_prefix(uint32_t node, std::vector<uint8_t> &out) const {

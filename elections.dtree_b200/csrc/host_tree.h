@@ -16,6 +16,10 @@ struct HostParams {
   bool vd = false;
   std::vector<double> depth_factors;  // irv_node.cpp:13-25; stale after set_min_depth (irv_node.h:127)
   void recompute_depth_factors();
+  // Checks a CSR batch of ballots (candidate indices) the way the Rcpp layer does before it updates
+  // (R_tree.cpp:24-43,139-151). On failure returns false with `err` set.
+  bool validate(const uint8_t *prefs, const uint64_t *offsets, uint64_t n, uint64_t *n_short, uint64_t *depth_mask,
+                std::string &err) const;
 };
 
 // CSR image of the trie, ready for upload, plus what the exports need.
@@ -43,12 +47,9 @@ class HostTree {
 
   explicit HostTree(const HostParams &p);
   void reset();
-  // Validates every ballot first; on failure returns false with `err` set and changes nothing.
-  bool update(const uint8_t *prefs, const uint64_t *offsets, uint64_t n, uint64_t *n_short, std::string &err);
-  uint64_t n_observed() const { return n_observed_; }
-  uint64_t depth_mask() const { return depth_mask_; }
+  // Inserts ballots [first, n) of a validated CSR batch (IRVNode::update once per ballot).
+  void insert_ballots(const uint8_t *prefs, const uint64_t *offsets, uint64_t first, uint64_t n);
   uint64_t n_nodes() const { return depth_.size(); }
-  uint64_t version() const { return version_; }  // bumped by update/reset
 
   void flatten(FlatTree &out) const;
 
@@ -60,7 +61,6 @@ class HostTree {
   std::vector<uint64_t> base_;
   std::vector<uint32_t> counts_;
   std::vector<int32_t> child_;
-  uint64_t n_observed_ = 0, depth_mask_ = 0, version_ = 0;
   int32_t new_node(uint32_t depth);
   void insert(const uint8_t *b, uint32_t len);
 };

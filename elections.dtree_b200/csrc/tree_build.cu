@@ -1,0 +1,411 @@
+// tree_build.cu — see tree_build.h. Level-synchronous construction: at depth d every observed ballot adds
+// one count to the slot its d-th preference (or its end) selects in its current node; slots that
+// received a count and may have children (irv_node.cpp:210-215) are numbered by a prefix sum, which
+// places the children of a level in breadth-first order — the order HostTree::flatten produces.
+#include "tree_build.h"
+
+#include <algorithm>
+
+namespace dtb {
+
+void DeviceTreeStore::release_all() {
+  node_base.release(); node_total.release(); slot_count.release(); obs_cnt.release(); obs_tally0.release();
+  slot_child.release(); slot_cand.release(); obs_first.release(); obs_key.release();
+  log_prefs.release(); log_slots.release(); log_off.release();
+  node_key.release(); cursor.release(); block_sums.release();
+  if (h_total) cudaFreeHost(h_total);
+  h_total = nullptr;
+  n_nodes = n_slots = n_obs = 0;
+  log_ballots = log_bytes = 0;
+}
+
+namespace {
+
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanBlock * kScanItems;
+constexpr uint32_t kDone = 0xFFFFFFFFu;
+
+struct TreePtrs {
+  uint32_t *node_base, *node_total, *slot_count;
+  int32_t *slot_child;
+  uint8_t *slot_cand;
+  uint64_t *node_key;
+};
+
+// Slot index of every preference of ballots [first, n): position of the candidate among the not yet
+// ranked ones, where ranking a candidate swaps it with the one at the front (irv_node.cpp:203-220).
+__global__ void slot_sequences_kernel(const uint8_t *__restrict__ prefs, const uint64_t *__restrict__ off,
+                                      uint8_t *__restrict__ slots, uint64_t first, uint64_t n, uint32_t nc) {
+  for (uint64_t b = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t lo = off[b];
+    const uint32_t len = (uint32_t)(off[b + 1] - lo);
+    const uint32_t L = min(len, nc - 1u);
+    uint8_t path[kMaxCandidates];
+    for (uint32_t i = 0; i < nc; ++i) path[i] = (uint8_t)i;
+    for (uint32_t d = 0; d < L; ++d) {
+      const uint8_t c = prefs[lo + d];
+      uint32_t i = d;
+      while (i < nc - 1u && path[i] != c) ++i;
+      slots[lo + d] = (uint8_t)(i - d);
+      path[i] = path[d];
+      path[d] = c;
+    }
+    for (uint32_t d = L; d < len; ++d) slots[lo + d] = 0;
+  }
+}
+
+__global__ void init_root_kernel(TreePtrs T, uint32_t *obs_tally0, uint32_t nc, int W) {
+  const uint32_t j = threadIdx.x;
+  if (j <= nc) {
+    T.slot_count[j] = 0;
+    T.slot_child[j] = -1;
+    T.slot_cand[j] = j < nc ? (uint8_t)j : 0xFF;
+  }
+  if (j < (uint32_t)kMaxCandidates) obs_tally0[j] = 0;
+  if (j < (uint32_t)W) T.node_key[j] = 0;
+  if (j == 0) {
+    T.node_base[0] = 0;
+    T.node_base[1] = nc + 1;
+  }
+}
+
+// One count per ballot still walking at `depth`; equal targets inside a warp are added once.
+__global__ void count_level_kernel(TreePtrs T, const uint64_t *__restrict__ off, const uint8_t *__restrict__ slots,
+                                   uint32_t *__restrict__ cursor, uint64_t n, uint32_t nc, uint32_t depth) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t idx = kDone;
+  if (b < n) {
+    const uint32_t cur = depth == 0 ? 0u : cursor[b];
+    if (cur != kDone) {
+      const uint32_t node = depth == 0 ? 0u : (uint32_t)T.slot_child[cur];
+      const uint32_t base = T.node_base[node], K = nc - depth;
+      const uint64_t lo = off[b];
+      const uint32_t len = (uint32_t)(off[b + 1] - lo);
+      if (len == depth) {  // irv_node.cpp:191-194
+        idx = base + K;
+        cursor[b] = kDone;
+      } else {
+        idx = base + slots[lo + depth];
+        cursor[b] = K == 2 ? kDone : idx;  // irv_node.cpp:210
+      }
+    } else if (depth == 0) {
+      cursor[b] = kDone;
+    }
+  }
+  const unsigned peers = __match_any_sync(0xFFFFFFFFu, idx);
+  if (idx != kDone && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&T.slot_count[idx], (uint32_t)__popc(peers));
+}
+
+// --- prefix sums over "how many things does element i produce" ---------------------------------
+
+// Slot i of a level (slots [slot_lo, slot_lo + n), K + 1 per node) gets a child when it is a child slot
+// with a count.
+struct LevelFlag {
+  const uint32_t *slot_count;
+  uint32_t slot_lo, per_node;  // per_node = K + 1
+  __device__ uint32_t operator()(uint32_t i) const {
+    return ((i % per_node) != per_node - 1u && slot_count[slot_lo + i] > 0u) ? 1u : 0u;
+  }
+};
+
+// Node i contributes its distinct observed ballots: those that stop there and, where the tree ends
+// (two candidates left), those that went on to either of them.
+struct ObservedFlag {
+  const uint32_t *node_base, *slot_count;
+  __device__ uint32_t operator()(uint32_t i) const {
+    const uint32_t base = node_base[i], K = node_base[i + 1] - base - 1u;
+    uint32_t f = slot_count[base + K] > 0u;
+    if (K == 2u) f += (slot_count[base] > 0u) + (slot_count[base + 1] > 0u);
+    return f;
+  }
+};
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+  __shared__ uint32_t warp_sums[kScanBlock / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  uint32_t before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < kScanBlock / 32; ++w) {
+    const uint32_t s = warp_sums[w];
+    if (w < warp) before += s;
+    all += s;
+  }
+  __syncthreads();
+  *total = all;
+  return before + x - v;
+}
+
+template <typename F>
+__global__ void __launch_bounds__(kScanBlock) tile_sums_kernel(F f, uint32_t n, uint32_t *__restrict__ block_sums) {
+  const uint32_t first = blockIdx.x * (uint32_t)kScanTile + threadIdx.x * (uint32_t)kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (first + k < n) s += f(first + k);
+  uint32_t total;
+  block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// Exclusive scan of the tile sums in place (one block), total to mapped host memory.
+__global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(uint32_t *__restrict__ block_sums, uint32_t nb,
+                                                               uint32_t *__restrict__ total_out) {
+  uint32_t carry = 0;
+  for (uint32_t start = 0; start < nb; start += kScanBlock) {
+    const uint32_t i = start + threadIdx.x;
+    const uint32_t v = i < nb ? block_sums[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, &total);
+    if (i < nb) block_sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+// Numbers the children of a level and initialises them: slots, candidates (the parent's order with the
+// taken candidate swapped to the front, irv_node.cpp:219), prefix key.
+__global__ void __launch_bounds__(kScanBlock)
+    create_children_kernel(TreePtrs T, LevelFlag f, uint32_t n, const uint32_t *__restrict__ block_sums,
+                           uint32_t level_first_node, uint32_t first_new_node, uint32_t new_slot_base, uint32_t n_new,
+                           uint32_t depth, int W) {
+  const uint32_t first = blockIdx.x * (uint32_t)kScanTile + threadIdx.x * (uint32_t)kScanItems;
+  uint32_t flags = 0, s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (first + k < n && f(first + k)) {
+      flags |= 1u << k;
+      ++s;
+    }
+  uint32_t total;
+  uint32_t rank = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+  const uint32_t K = f.per_node - 1u;  // children of a parent; a child has K - 1 children + stop = K slots
+  for (int k = 0; k < kScanItems; ++k) {
+    if (!(flags >> k & 1u)) continue;
+    const uint32_t i = first + k, pn = i / f.per_node, j = i % f.per_node;
+    const uint32_t slot = f.slot_lo + i, pbase = f.slot_lo + pn * f.per_node;
+    const uint32_t child = first_new_node + rank, cbase = new_slot_base + rank * K;
+    ++rank;
+    T.slot_child[slot] = (int32_t)child;
+    T.node_base[child] = cbase;
+    for (uint32_t q = 0; q + 1 < K; ++q) {
+      T.slot_cand[cbase + q] = (q + 1 == j) ? T.slot_cand[pbase] : T.slot_cand[pbase + q + 1];
+      T.slot_child[cbase + q] = -1;
+      T.slot_count[cbase + q] = 0;
+    }
+    T.slot_cand[cbase + K - 1] = 0xFF;
+    T.slot_child[cbase + K - 1] = -1;
+    T.slot_count[cbase + K - 1] = 0;
+    const uint32_t parent = level_first_node + pn;
+    const uint64_t cand = T.slot_cand[slot];
+    for (int w = 0; w < W; ++w) {
+      uint64_t key = T.node_key[(size_t)parent * W + w];
+      if ((int)(depth / kPrefsPerWord) == w) key |= cand << (kPrefBits * (depth % kPrefsPerWord));
+      T.node_key[(size_t)child * W + w] = key;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) T.node_base[first_new_node + n_new] = new_slot_base + n_new * K;
+}
+
+__global__ void node_totals_kernel(TreePtrs T, uint32_t n_nodes) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const uint32_t base = T.node_base[i], K = T.node_base[i + 1] - base - 1u;
+  uint32_t s = 0;
+  for (uint32_t j = 0; j < K; ++j) s += T.slot_count[base + j];
+  T.node_total[i] = s;
+}
+
+struct ObsOut {
+  uint64_t *key;
+  uint32_t *cnt, *tally0;
+  uint8_t *first;
+};
+
+__device__ void write_observed(const TreePtrs &T, const ObsOut &O, uint32_t at, uint32_t node, uint32_t depth, int extra_cand,
+                               uint32_t count, uint32_t nc, int W) {
+  BallotKey<kMaxKeyWords> k;
+  for (int w = 0; w < kMaxKeyWords; ++w) k.w[w] = w < W ? T.node_key[(size_t)node * W + w] : 0ull;
+  uint32_t L = depth;
+  if (extra_cand >= 0) key_set<kMaxKeyWords>(k, (int)L++, (uint32_t)extra_cand);
+  uint32_t first = 0xFFu;
+  if (L > 0) {
+    first = key_get<kMaxKeyWords>(k, 0);
+    for (uint32_t j = L; j < nc - 1u; ++j) key_set<kMaxKeyWords>(k, (int)j, first);  // capi.cu pack_ballot
+    atomicAdd(&O.tally0[first], count);
+  }
+  for (int w = 0; w < W; ++w) O.key[(size_t)at * W + w] = k.w[w];
+  O.cnt[at] = count;
+  O.first[at] = (uint8_t)first;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+    write_observed_kernel(TreePtrs T, ObservedFlag f, uint32_t n_nodes, const uint32_t *__restrict__ block_sums, ObsOut O,
+                          uint32_t nc, int W) {
+  const uint32_t first = blockIdx.x * (uint32_t)kScanTile + threadIdx.x * (uint32_t)kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (first + k < n_nodes) s += f(first + k);
+  uint32_t total;
+  uint32_t at = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+  if (s == 0) return;
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint32_t i = first + k;
+    if (i >= n_nodes) break;
+    const uint32_t base = T.node_base[i], K = T.node_base[i + 1] - base - 1u, depth = nc - K;
+    const uint32_t stop = T.slot_count[base + K];
+    if (stop) write_observed(T, O, at++, i, depth, -1, stop, nc, W);
+    if (K == 2u)
+      for (uint32_t j = 0; j < 2u; ++j) {
+        const uint32_t c = T.slot_count[base + j];
+        if (c) write_observed(T, O, at++, i, depth, (int)T.slot_cand[base + j], c, nc, W);
+      }
+  }
+}
+
+#define BUILD_TRY(expr)              \
+  do {                               \
+    cudaError_t e_ = (expr);         \
+    if (e_ != cudaSuccess) return e_; \
+  } while (0)
+
+TreePtrs ptrs(DeviceTreeStore &S) {
+  return TreePtrs{S.node_base.p, S.node_total.p, S.slot_count.p, S.slot_child.p, S.slot_cand.p, S.node_key.p};
+}
+
+cudaError_t grow_nodes(DeviceTreeStore &S, size_t nodes, size_t keep_nodes, int W, cudaStream_t s) {
+  BUILD_TRY(S.node_base.grow(nodes + 1, keep_nodes + 1, s));
+  BUILD_TRY(S.node_key.grow(nodes * W, keep_nodes * W, s));
+  return cudaSuccess;
+}
+
+cudaError_t grow_slots(DeviceTreeStore &S, size_t slots, size_t keep, cudaStream_t s) {
+  BUILD_TRY(S.slot_count.grow(slots, keep, s));
+  BUILD_TRY(S.slot_child.grow(slots, keep, s));
+  BUILD_TRY(S.slot_cand.grow(slots, keep, s));
+  return cudaSuccess;
+}
+
+}  // namespace
+
+cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t *h_prefs, const uint64_t *h_offsets,
+                                 uint64_t n_ballots, cudaStream_t stream, BuildStats *stats, bool *too_big) {
+  const int W = key_words_for(nc);
+  BuildStats st;
+  if (too_big) *too_big = false;
+  if (!S.h_total) {
+    BUILD_TRY(cudaHostAlloc((void **)&S.h_total, 2 * sizeof(uint32_t), cudaHostAllocMapped));
+  }
+  uint32_t *d_total = nullptr;
+  BUILD_TRY(cudaHostGetDevicePointer((void **)&d_total, S.h_total, 0));
+
+  // 1. append the new part of the ballot log and compute its slot sequences
+  if (n_ballots < S.log_ballots) S.log_ballots = S.log_bytes = 0;  // the log was reset
+  if (n_ballots > S.log_ballots) {
+    const uint64_t old_b = S.log_ballots, old_bytes = S.log_bytes, bytes = h_offsets[n_ballots];
+    BUILD_TRY(S.log_prefs.grow(bytes, old_bytes, stream));
+    BUILD_TRY(S.log_slots.grow(bytes, old_bytes, stream));
+    BUILD_TRY(S.log_off.grow(n_ballots + 1, old_b + 1, stream));
+    if (bytes > old_bytes)
+      BUILD_TRY(cudaMemcpyAsync(S.log_prefs.p + old_bytes, h_prefs + old_bytes, bytes - old_bytes, cudaMemcpyHostToDevice, stream));
+    BUILD_TRY(cudaMemcpyAsync(S.log_off.p + old_b, h_offsets + old_b, (n_ballots - old_b + 1) * sizeof(uint64_t),
+                              cudaMemcpyHostToDevice, stream));
+    st.h2d_bytes += (bytes - old_bytes) + (n_ballots - old_b + 1) * sizeof(uint64_t);
+    const uint64_t fresh = n_ballots - old_b;
+    const int grid = (int)std::min<uint64_t>((fresh + 127) / 128, 1u << 16);
+    slot_sequences_kernel<<<grid, 128, 0, stream>>>(S.log_prefs.p, S.log_off.p, S.log_slots.p, old_b, n_ballots, nc);
+    ++st.launches;
+    S.log_ballots = n_ballots;
+    S.log_bytes = bytes;
+  }
+
+  // 2. root
+  size_t nodes_guess = std::max<size_t>({(size_t)S.n_nodes + S.n_nodes / 4, (size_t)std::min<uint64_t>(n_ballots, 1u << 24), 64});
+  BUILD_TRY(grow_nodes(S, nodes_guess, 0, W, stream));
+  BUILD_TRY(grow_slots(S, std::max<size_t>((size_t)S.n_slots + S.n_slots / 4, nodes_guess * 4 + nc + 1), 0, stream));
+  BUILD_TRY(S.obs_tally0.reserve(kMaxCandidates));
+  BUILD_TRY(S.cursor.reserve(std::max<uint64_t>(n_ballots, 1)));
+  init_root_kernel<<<1, 64, 0, stream>>>(ptrs(S), S.obs_tally0.p, nc, W);
+  ++st.launches;
+
+  // 3. one level at a time
+  uint32_t n_nodes = 1, n_slots = nc + 1, level_first = 0, level_nodes = 1;
+  S.level_first[0] = 0;
+  uint32_t depth = 0;
+  const int ballot_grid = (int)((n_ballots + 255) / 256);
+  for (;; ++depth) {
+    const uint32_t K = nc - depth;
+    if (n_ballots > 0) {
+      count_level_kernel<<<ballot_grid, 256, 0, stream>>>(ptrs(S), S.log_off.p, S.log_slots.p, S.cursor.p, n_ballots, nc, depth);
+      ++st.launches;
+    }
+    if (K <= 2 || n_ballots == 0) break;  // irv_node.cpp:210: a node with two candidates left has no children
+    const uint32_t slot_lo = n_slots - level_nodes * (K + 1), n_level_slots = level_nodes * (K + 1);
+    const uint32_t nb = (n_level_slots + kScanTile - 1) / kScanTile;
+    BUILD_TRY(S.block_sums.reserve(nb));
+    LevelFlag f{S.slot_count.p, slot_lo, K + 1};
+    tile_sums_kernel<<<nb, kScanBlock, 0, stream>>>(f, n_level_slots, S.block_sums.p);
+    scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(S.block_sums.p, nb, d_total);
+    st.launches += 2;
+    BUILD_TRY(cudaStreamSynchronize(stream));
+    const uint32_t n_new = S.h_total[0];
+    if (n_new == 0) break;
+    const uint64_t want_slots = (uint64_t)n_slots + (uint64_t)n_new * K;
+    if (want_slots >= 0xFFFFFFF0ull) {
+      if (too_big) *too_big = true;
+      return cudaSuccess;
+    }
+    BUILD_TRY(grow_nodes(S, (size_t)n_nodes + n_new, n_nodes, W, stream));
+    BUILD_TRY(grow_slots(S, want_slots, n_slots, stream));
+    f.slot_count = S.slot_count.p;
+    create_children_kernel<<<nb, kScanBlock, 0, stream>>>(ptrs(S), f, n_level_slots, S.block_sums.p, level_first, n_nodes, n_slots,
+                                                          n_new, depth, W);
+    ++st.launches;
+    level_first = n_nodes;
+    level_nodes = n_new;
+    n_nodes += n_new;
+    n_slots = (uint32_t)want_slots;
+    S.level_first[depth + 1] = level_first;
+  }
+  S.n_levels = depth + 1;
+  S.level_first[S.n_levels] = n_nodes;
+  st.levels = S.n_levels;
+
+  // 4. per-node totals and the observed multiset
+  BUILD_TRY(S.node_total.reserve(n_nodes));
+  node_totals_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(ptrs(S), n_nodes);
+  const uint32_t nb = (n_nodes + kScanTile - 1) / kScanTile;
+  BUILD_TRY(S.block_sums.reserve(nb));
+  ObservedFlag of{S.node_base.p, S.slot_count.p};
+  tile_sums_kernel<<<nb, kScanBlock, 0, stream>>>(of, n_nodes, S.block_sums.p);
+  scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(S.block_sums.p, nb, d_total);
+  st.launches += 3;
+  BUILD_TRY(cudaStreamSynchronize(stream));
+  const uint32_t n_obs = S.h_total[0];
+  BUILD_TRY(S.obs_key.reserve((size_t)std::max(n_obs, 1u) * W));
+  BUILD_TRY(S.obs_cnt.reserve(std::max(n_obs, 1u)));
+  BUILD_TRY(S.obs_first.reserve(std::max(n_obs, 1u)));
+  if (n_obs) {
+    ObsOut O{S.obs_key.p, S.obs_cnt.p, S.obs_tally0.p, S.obs_first.p};
+    write_observed_kernel<<<nb, kScanBlock, 0, stream>>>(ptrs(S), of, n_nodes, S.block_sums.p, O, nc, W);
+    ++st.launches;
+  }
+  BUILD_TRY(cudaGetLastError());
+  BUILD_TRY(cudaStreamSynchronize(stream));
+  S.n_nodes = n_nodes;
+  S.n_slots = n_slots;
+  S.n_obs = n_obs;
+  if (stats) *stats = st;
+  return cudaSuccess;
+}
+
+}  // namespace dtb

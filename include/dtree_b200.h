@@ -75,7 +75,10 @@ uint32_t dtree_depth_factors(const dtree_t *t, double *out, uint32_t cap);
  * dirichlet_tree.h:182-193 -> IRVNode::update, irv_node.cpp:176-221. Every ballot counts once
  * (R_tree.cpp:38). Fails with DTREE_ERR_ARG, changing nothing, if a ballot repeats a candidate
  * or names one >= n_candidates. *n_short (may be NULL) receives how many ballots had
- * 0 < length < min_depth, for the host layer's warning (R_tree.cpp:139-147). */
+ * 0 < length < min_depth, for the host layer's warning (R_tree.cpp:139-147).
+ * The call validates the ballots and appends them to the handle's ballot log; the count tree itself is
+ * built on the device, from that log, by the next sampling call or dtree_sync_device (tree_build.cu:
+ * one pass per tree level instead of one pointer walk + std::map insert per ballot). */
 int dtree_update(dtree_t *t, const uint8_t *prefs, const uint64_t *offsets, uint64_t n_ballots,
                  uint64_t *n_short);
 /* RDirichletTree::reset, R_tree.cpp:119-123 */
@@ -137,8 +140,10 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
  * failure (DTREE_ERR_CUDA) if there was one and refreshes dtree_last_stats. */
 int dtree_sample_posterior_finish(dtree_t *t, void *stream);
 
-/* Uploads the device mirror of the tree now (otherwise done lazily by the first sample after an
- * update/reset). dtree_invalidate_device drops it, so that the next sample pays the upload. */
+/* Builds the device mirror of the tree now (otherwise done lazily by the first sample after an
+ * update/reset): uploads the part of the ballot log the device has not seen and rebuilds the level-ordered
+ * arrays there. dtree_invalidate_device drops mirror and device log, so that the next sample starts from
+ * host memory again. */
 int dtree_sync_device(dtree_t *t);
 int dtree_invalidate_device(dtree_t *t);
 
@@ -178,14 +183,17 @@ int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user
  *        -1 (default) picks 2 when there are enough elections to fill the GPU with one per thread, else 1,
  *        and 0 only if the worst-case scratch of 1/2 does not fit the device. All give bit-identical outcomes;
  *      "block_threads" (0 = auto), "blocks_per_sm" (0 = auto), "urn_max" (largest count split by the
- *        Polya-urn shortcut instead of Gamma variates, <= 8).
+ *        Polya-urn shortcut instead of Gamma variates, <= 8);
+ *      "host_build" (0 default; 1 = build the tree with the host trie and upload it, the pre-device-build
+ *        path, kept to measure against; the two mirrors are identical array for array).
  * Returns DTREE_ERR_ARG for an unknown key. */
 int dtree_set_tuning(dtree_t *t, const char *key, int64_t value);
 /* Statistics of the last sampling call on this handle:
  *  [0] kernel launches, [1] elections simulated, [2] sampled entries written, [3] frontier items
  *  processed, [4] Gamma variates drawn, [5] binomial variates drawn, [6] IRV entry re-reads,
  *  [7] device bytes of scratch, [8] H2D bytes, [9] D2H bytes, [10] outcome slots read,
- *  [11] nodes split by the urn shortcut, [12] mode used, [13] elections re-run in a worst-case arena. */
+ *  [11] nodes split by the urn shortcut, [12] mode used, [13] elections re-run in a worst-case arena,
+ *  [14] kernel launches of the last device tree build. */
 int dtree_last_stats(const dtree_t *t, uint64_t *out, uint32_t cap);
 
 #ifdef __cplusplus

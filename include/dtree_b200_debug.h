@@ -23,6 +23,14 @@ int dtree_debug_gamma(double alpha, int log_space, uint64_t seed, uint32_t n, fl
 /* n independent Binomial(n_trials, p) variates, 0 <= p <= 1. */
 int dtree_debug_binomial(uint32_t n_trials, double p, uint64_t seed, uint32_t n, uint32_t *out, int device);
 
+/* Copies one array of the handle's device mirror back to the host (building the mirror first if it is
+ * stale). which: 0 node_base u32[n_nodes+1], 1 node_total u32[n_nodes], 2 slot_count u32[n_slots],
+ * 3 slot_child i32[n_slots], 4 slot_cand u8[n_slots], 5 obs_key u64[n_obs*W], 6 obs_cnt u32[n_obs],
+ * 7 obs_first u8[n_obs], 8 obs_tally0 u32[32]. *needed_bytes receives the array size; the copy happens
+ * only if cap_bytes is large enough. Used to check the device-built tree against the host trie. */
+struct dtree;
+int dtree_debug_device_image(struct dtree *t, int which, void *out, uint64_t cap_bytes, uint64_t *needed_bytes);
+
 #ifdef __cplusplus
 }
 #endif
