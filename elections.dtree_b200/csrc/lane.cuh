@@ -29,8 +29,12 @@ struct LaneState {
   uint32_t n_big;             // big-count stack depth
   uint32_t eliminated;
   uint32_t hw_queue, hw_big;
+  uint32_t unresolved;        // ballots (sampled + observed) inside the nodes waiting in the small-count queue
   bool overflow;
 };
+
+// A queued or parked node carries the number of ballots inside it in the (otherwise unused) prefix word.
+__device__ __forceinline__ uint32_t lane_mass(const DItem &x) { return (uint32_t)x.prefix.w[0]; }
 
 template <int BLOCK>
 struct LaneShared {
@@ -46,6 +50,7 @@ __device__ __forceinline__ void lane_enqueue(const SimArgs &a, const DeferredScr
   } else {
     if (st.q_tail - st.q_head < cp.queue) sc.queue[(st.q_tail++) % cp.queue] = ch;
     else st.overflow = true;
+    st.unresolved += lane_mass(ch);
     st.hw_queue = max(st.hw_queue, st.q_tail - st.q_head);
   }
 }
@@ -54,13 +59,13 @@ __device__ __forceinline__ void lane_enqueue(const SimArgs &a, const DeferredScr
 template <int BLOCK>
 __device__ __forceinline__ void lane_route(const SimArgs &a, LaneShared<BLOCK> &sh, const DeferredScratch &sc,
                                            const DeferredCaps &cp, LaneState &st, const DItem &x, uint32_t depth,
-                                           uint32_t cand, uint32_t tot, uint32_t cs, int32_t child, bool has_obs) {
+                                           uint32_t cand, uint32_t tot, uint32_t cs, int32_t child, uint32_t obs) {
   const bool standing = !(st.eliminated >> cand & 1u);
   if (standing) sh.tally[cand][threadIdx.x] += tot;
-  const bool cont = cs > 0u || (has_obs && child >= 0);
+  const bool cont = cs > 0u || (obs > 0u && child >= 0);
   if (!cont) return;
   DItem ch;
-  ch.prefix.w[0] = 0;
+  ch.prefix.w[0] = cs + (child >= 0 ? obs : 0u);  // sampled ballots that go on + observed ones below
   ch.node_key = child_node_key(x.node_key, cand);
   ch.count = cs;
   ch.node = child;
@@ -108,7 +113,7 @@ __device__ __forceinline__ void lane_split_small(const SimArgs &a, LaneShared<BL
       const uint32_t obs = a.T.slot_count[nb + slot];
       if (c + obs == 0u) continue;
       lane_route<BLOCK>(a, sh, sc, cp, st, x, depth, a.T.slot_cand[nb + slot], c + obs, lv.leaf_children ? 0u : c,
-                        a.T.slot_child[nb + slot], obs > 0u);
+                        a.T.slot_child[nb + slot], obs);
     }
   } else {
     uint32_t done = 0;
@@ -126,7 +131,7 @@ __device__ __forceinline__ void lane_split_small(const SimArgs &a, LaneShared<BL
       if (slot == lv.K) continue;
       const uint32_t cand = nb != 0xFFFFFFFFu ? (uint32_t)a.T.slot_cand[nb + slot] : nth_unused(x.used, nc, slot);
       const int32_t child = nb != 0xFFFFFFFFu ? a.T.slot_child[nb + slot] : -1;
-      lane_route<BLOCK>(a, sh, sc, cp, st, x, depth, cand, c, lv.leaf_children ? 0u : c, child, false);
+      lane_route<BLOCK>(a, sh, sc, cp, st, x, depth, cand, c, lv.leaf_children ? 0u : c, child, 0u);
     }
   }
 }
@@ -216,7 +221,7 @@ __device__ void lane_split_big(const SimArgs &a, LaneShared<BLOCK> &sh, const De
       cand = nth_unused(x.used, nc, slot);
     }
     if (c + obs == 0u) continue;
-    lane_route<BLOCK>(a, sh, sc, cp, st, x, depth, cand, c + obs, lv.leaf_children ? 0u : c, child, obs > 0u);
+    lane_route<BLOCK>(a, sh, sc, cp, st, x, depth, cand, c + obs, lv.leaf_children ? 0u : c, child, obs);
   }
 }
 
@@ -250,12 +255,12 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
     const RngKey key = election_key(a.seed, a.first_election + e);
     LaneState st;
     st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.eliminated = 0;
-    st.hw_queue = 0; st.hw_big = 0; st.overflow = false;
+    st.hw_queue = 0; st.hw_big = 0; st.unresolved = 0; st.overflow = false;
 #pragma unroll 1
     for (uint32_t c = 0; c < nc; ++c) sh.tally[c][tid] = 0;
     if (active) {
       DItem root;
-      root.prefix.w[0] = 0;
+      root.prefix.w[0] = a.n_sample;
       root.node_key = kRootNodeKey;
       root.count = a.n_sample;
       root.node = 0;
@@ -265,71 +270,96 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
     }
     bool decided = !active;
     // Pass -1 splits the root; pass r >= 0 eliminates a candidate, then splits what was parked under it.
+    // Nodes with a small sampled count are NOT split as they appear: they wait in the small-count queue, their
+    // ballots counted in st.unresolved, and a round is decided as soon as its outcome cannot depend on where those
+    // ballots go (they can only add to tallies): the weakest candidate stays weakest if its tally plus all
+    // unresolved ballots is still below every other tally. Only while that is not the case are waiting nodes
+    // split, oldest first. Every split is a pure function of the node, so which of them are carried out changes
+    // no outcome: elimination orders and winners are those of the eager evaluation (deferred_kernel, simulate_kernel).
     for (int pass = -1; pass < (int)n_rounds; ++pass) {
-      if (pass >= 0 && !decided && !st.overflow) {
-        const uint32_t round = (uint32_t)pass;
-        uint32_t mn = 0xFFFFFFFFu, tied = 0, ntied = 0, total = 0, top = 0, top_c = 0;
-#pragma unroll 1
-        for (uint32_t c = 0; c < nc; ++c) {
-          if (st.eliminated >> c & 1u) continue;
-          const uint32_t t = sh.tally[c][tid];
-          if (t < mn) { mn = t; tied = 1u << c; ntied = 1; }
-          else if (t == mn) { tied |= 1u << c; ++ntied; }
-          total += t;
-          if (t > top) { top = t; top_c = c; }
+      if (pass < 0) {
+        // a root with a small sampled count is split at once (it holds every ballot)
+        const bool small_root = active && st.q_head < st.q_tail;
+        if (small_root) {
+          const DItem x = sc.queue[(st.q_head++) % cp.queue];
+          st.unresolved -= lane_mass(x);
+          lane_split_small<BLOCK>(a, sh, sc, cp, st, x, key, stat);
         }
-        if (early_stop && top > total - top) {
-          st.eliminated = ~(1u << top_c) & cand_mask;
-          decided = true;
-        } else {
-          if (ntied > 1u) {
-            U4 r = node_random(key, 0ull, kStreamTie, round);
-            const uint32_t pick = uniform_below(r.x, ntied);
-            for (uint32_t k = 0; k < pick; ++k) tied &= tied - 1u;
-          }
-          const uint32_t chosen = (uint32_t)__ffs(tied) - 1u;
-          if (a.elim_orders) a.elim_orders[(uint64_t)e * nc + round] = (uint8_t)chosen;
-          st.eliminated |= 1u << chosen;
-          if (mn != 0u && round + 1u != n_rounds) {
-            // queue the nodes parked under the eliminated candidate
-            const uint32_t np = min(st.n_pool, cp.pool);
-            const uint32_t n_vec = (np + 15u) / 16u;
-            const uint32_t pattern = chosen * 0x01010101u;
+      } else {
+        const uint32_t round = (uint32_t)pass;
+        bool pending = !decided && !st.overflow;  // this lane still has to settle the round
+        for (;;) {
+          bool uncertain = false;
+          if (pending) {
+            uint32_t mn = 0xFFFFFFFFu, second = 0xFFFFFFFFu, tied = 0, ntied = 0, total = 0, top = 0, top_c = 0;
 #pragma unroll 1
-            for (uint32_t v = 0; v < n_vec; ++v) {
-              const uint4 h = reinterpret_cast<const uint4 *>(sc.holder)[v];
-              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-              uint32_t hits = 0;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint32_t eq = __vcmpeq4(hw[q], pattern);
-                hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * q);
+            for (uint32_t c = 0; c < nc; ++c) {
+              if (st.eliminated >> c & 1u) continue;
+              const uint32_t t = sh.tally[c][tid];
+              if (t < mn) { second = mn; mn = t; tied = 1u << c; ntied = 1; }
+              else if (t == mn) { tied |= 1u << c; ++ntied; }
+              else if (t < second) second = t;
+              total += t;
+              if (t > top) { top = t; top_c = c; }
+            }
+            const uint32_t u = st.unresolved;
+            if (early_stop && top - u > total - top && top > u) {
+              st.eliminated = ~(1u << top_c) & cand_mask;
+              decided = true;
+              pending = false;
+            } else if (u != 0u && (ntied > 1u || mn + u >= second)) {
+              uncertain = true;
+            } else {
+              pending = false;
+              if (ntied > 1u) {
+                U4 r = node_random(key, 0ull, kStreamTie, round);
+                const uint32_t pick = uniform_below(r.x, ntied);
+                for (uint32_t k = 0; k < pick; ++k) tied &= tied - 1u;
               }
-              while (hits) {
-                const uint32_t j = v * 16u + (uint32_t)__ffs(hits) - 1u;
-                hits &= hits - 1u;
-                if (j >= np) break;
-                sc.holder[j] = 0xFF;
-                const DItem x = sc.pool[j];
-                lane_enqueue(a, sc, cp, st, x);
-                sc.free_list[st.n_free++] = j;
+              const uint32_t chosen = (uint32_t)__ffs(tied) - 1u;
+              if (a.elim_orders) a.elim_orders[(uint64_t)e * nc + round] = (uint8_t)chosen;
+              st.eliminated |= 1u << chosen;
+              if (mn != 0u && round + 1u != n_rounds) {
+                // queue the nodes parked under the eliminated candidate
+                const uint32_t np = min(st.n_pool, cp.pool);
+                const uint32_t n_vec = (np + 15u) / 16u;
+                const uint32_t pattern = chosen * 0x01010101u;
+#pragma unroll 1
+                for (uint32_t v = 0; v < n_vec; ++v) {
+                  const uint4 h = reinterpret_cast<const uint4 *>(sc.holder)[v];
+                  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+                  uint32_t hits = 0;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const uint32_t eq = __vcmpeq4(hw[q], pattern);
+                    hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * q);
+                  }
+                  while (hits) {
+                    const uint32_t j = v * 16u + (uint32_t)__ffs(hits) - 1u;
+                    hits &= hits - 1u;
+                    if (j >= np) break;
+                    sc.holder[j] = 0xFF;
+                    const DItem x = sc.pool[j];
+                    lane_enqueue(a, sc, cp, st, x);
+                    sc.free_list[st.n_free++] = j;
+                  }
+                }
               }
             }
           }
-        }
-      }
-      // drain: small nodes first (short), then one big node per turn; lanes wait for each other per turn
-      for (;;) {
-        const bool has_small = !decided && !st.overflow && st.q_head < st.q_tail;
-        const bool has_big = !decided && !st.overflow && st.n_big > 0;
-        if (!__any_sync(0xffffffffu, has_small || has_big)) break;
-        if (__any_sync(0xffffffffu, has_small)) {
-          if (has_small) {
+          if (!__any_sync(0xffffffffu, uncertain)) break;
+          if (uncertain && !st.overflow) {
             const DItem x = sc.queue[(st.q_head++) % cp.queue];
+            st.unresolved -= lane_mass(x);
             lane_split_small<BLOCK>(a, sh, sc, cp, st, x, key, stat);
           }
-          continue;
+          if (st.overflow) pending = false;
         }
+      }
+      // big nodes are always split: one per turn, lanes wait for each other per turn
+      for (;;) {
+        const bool has_big = !decided && !st.overflow && st.n_big > 0;
+        if (!__any_sync(0xffffffffu, has_big)) break;
         if (has_big) {
           const DItem x = sc.big[0][--st.n_big];
           lane_split_big<BLOCK, LOG>(a, sh, sc, cp, st, x, key, row, stat);
