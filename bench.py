@@ -206,6 +206,8 @@ def main():
     wins = torch.zeros(nc, dtype=torch.int64, device=dev)
 
     total = torch.zeros(nc, dtype=torch.int64, device=dev)
+    # Larger than the 126 MB L2: zeroed between timed steps so that no step starts with the previous one's lines.
+    l2_flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
         if world > 1:
@@ -239,8 +241,11 @@ def main():
         kernel_ev = []
         total.zero_()
         ev0.record(stream)
+        step_ev = []
         for i in range(steps):
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l2_flush.zero_()  # between timed steps, not inside one
+            s0, k0, k1, s1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            s0.record(stream)
             k0.record(stream)
             launch(warmup + i)
             k1.record(stream)
@@ -248,18 +253,23 @@ def main():
             if world > 1:
                 dist.all_reduce(wins, op=dist.ReduceOp.SUM)
             total.add_(wins)
+            s1.record(stream)
+            step_ev.append((s0, s1))
         ev1.record(stream)
         barrier()
         N.check(L.dtree_sample_posterior_finish(t._h, stream.cuda_stream))
         st = t.last_stats()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        # a step = kernel(s) + all-reduce + accumulation; the K steps are timed one by one because the L2 flush sits
+        # between them; the job's time is the sum, max over ranks
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in step_ev), ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = float(ms.item())
+        ms, ms_with_flush = float(ms[0].item()), float(ms[1].item())
         assert int(total.sum().item()) == n_el * world * steps
-        return {"value": n_el * world * steps / (ms / 1e3), "elapsed_ms": ms, "steps": steps, "elections_per_gpu": n_el,
+        return {"value": n_el * world * steps / (ms / 1e3), "elapsed_ms": ms, "elapsed_ms_with_flush": ms_with_flush,
+                "steps": steps, "elections_per_gpu": n_el,
                 "kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in kernel_ev])),
-                "kernel_ms_steps": [round(a.elapsed_time(b), 2) for a, b in kernel_ev], "stats": st,
+                "kernel_ms_steps": [round(a.elapsed_time(b), 3) for a, b in kernel_ev], "stats": st,
                 "kernel": {0: "simulate_kernel", 1: "deferred_kernel", 2: "lane_kernel"}[st["mode"]]}
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -386,8 +396,8 @@ def main():
                                         "above 1.0 because this kernel provably never touches those bytes (it splits %.0f nodes per "
                                         "election where a full expansion visits %.0f), not a bandwidth claim"
                                         % (st["items"] / per_el, denominators.get("kernel_counters", {}).get("items_full", float("nan")))}
-            out["limiter"] = ("instruction issue / divergence, not HBM (profiles/r01f_ncu_lane_kernel_c3.txt, "
-                              "profiles/r01e_ncu_deferred_kernel_c3.txt)")
+            out["limiter"] = ("instruction issue and latency of dependent f32/f64 arithmetic in the Gamma / binomial samplers, "
+                              "not HBM (profiles/r01i_ncu_lane_kernel_c3.txt, profiles/r01e_ncu_deferred_kernel_c3.txt)")
         return out
 
     rl = roofline(main)
@@ -398,8 +408,9 @@ def main():
         "dtype": "f32 Gamma variates + f64 binomial rejection; u32 counts/tallies", "data": "synthetic",
         "config": {"workload": describe(name, cfg, epg), "global_elections_per_step": epg * world,
                    "kernel": main["kernel"],
-                   "cache": "per-election scratch far larger than L2 (%.1f GB reserved); nothing is reused between elections"
-                            % (stats["scratch_bytes"] / 1e9),
+                   "cache": "L2 flushed between timed steps (a 512 MB buffer is zeroed outside the per-step event pairs; "
+                            "%.2f ms for the %d steps with the flushes included); per-election scratch %.1f GB reserved, "
+                            "nothing is reused between elections" % (main["elapsed_ms_with_flush"], args.steps, stats["scratch_bytes"] / 1e9),
                    "parallelism": "elections sharded over %d GPU(s), tree replicated, one all-reduce of %d win counts" % (world, nc),
                    "seed": SEED},
         "e2e": e2e, "gpu_launches": int(stats["launches"]) * args.steps,

@@ -530,13 +530,16 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     // is replayed by deferred_kernel in a worst-case arena.
     if (!hit || 4ull * z.pool > 3ull * z.lane_pool) z.lane_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 3ull * z.pool + 512);
     if (!hit || 4ull * z.queue > 3ull * z.lane_queue) z.lane_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 3ull * z.queue + 512);
-    if (!hit || 4ull * z.big > 3ull * z.lane_big) z.lane_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 3ull * z.big + 64);
+    // (the lane kernel's heap also holds small-count nodes that carry many observed ballots, which the pilot's warp
+    // kernel keeps in its small-count queue: size it for both)
+    const uint64_t lane_heap = (uint64_t)z.big + z.queue;
+    if (!hit || 4ull * lane_heap > 3ull * z.lane_big) z.lane_big = (uint32_t)std::min<uint64_t>(pl.arena_items, 3ull * lane_heap + 64);
     Plan lp = pl;
     lp.lane = true;
     lp.block = 128;
     lp.cap_items = std::min(z.lane_pool, pl.arena_items);
     lp.cap_queue = std::min(z.lane_queue, pl.arena_queue);
-    lp.cap_big = std::min(z.lane_big, pl.arena_big);
+    lp.cap_big = std::min(z.lane_big, pl.arena_items);
     lp.stride = (deferred_scratch_bytes(lp.cap_items, lp.cap_queue, lp.cap_big) + 255) & ~255ull;  // per thread
     lp.stride_block = lp.stride * lp.block;
     {

@@ -43,9 +43,14 @@ struct DeferredWarp {
   uint32_t n_pool;    // high-water mark of the parked-node pool
   int32_t n_free;     // free-list depth (may dip below 0 while lanes race for the last free slots)
   uint32_t q_tail;    // small-count work queue (circular, monotone counters; q_head is a register)
-  uint32_t big_tail;  // big-count list being filled
+  uint32_t big_tail;  // big-count list of waiting nodes (big[0])
   uint32_t overflow;
+  uint32_t unresolved;      // ballots (sampled + observed) inside the waiting nodes
+  uint32_t small_mass_max;  // largest number of ballots any node in the small-count queue has had
 };
+
+// A waiting or parked node carries the number of ballots inside it in the (otherwise unused) prefix word.
+__device__ __forceinline__ uint32_t node_mass(const DItem &x) { return (uint32_t)x.prefix.w[0]; }
 
 // Per-warp scratch. Parked nodes live in `pool` (slot reuse through `free_list`), with the candidate they
 // are parked under in `holder` (0xFF = free slot). Nodes being split in the current round are transient:
@@ -73,14 +78,17 @@ struct DeferredScratch {
   }
 };
 
-// Puts a node that must be split in the current round on the right transient list.
+// Puts a node whose candidate is out on the waiting list for its kind of split (big[0] or the circular queue).
 __device__ __forceinline__ void enqueue_node(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
-                                             const DeferredCaps &cp, const DItem &ch, int big_sel) {
+                                             const DeferredCaps &cp, const DItem &ch) {
+  const uint32_t m = node_mass(ch);
+  atomicAdd(&ws.unresolved, m);
   if (ch.count > a.urn_max) {
     const uint32_t q = coalesced_reserve(&ws.big_tail);
-    if (q < cp.big) sc.big[big_sel][q] = ch;
+    if (q < cp.big) sc.big[0][q] = ch;
     else ws.overflow = 1;
   } else {
+    atomicMax(&ws.small_mass_max, m);
     const uint32_t q = coalesced_reserve(&ws.q_tail);
     if (q - ws.q_head < cp.queue) sc.queue[q % cp.queue] = ch;  // q_head only grows: the test is conservative
     else ws.overflow = 1;
@@ -92,20 +100,20 @@ __device__ __forceinline__ void enqueue_node(const SimArgs &a, DeferredWarp &ws,
 // sampled ballots that continue below the child, `child` is the child's CSR node (-1: none).
 static __device__ __noinline__ void route_child(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
                                             const DeferredCaps &cp, const DItem &x, uint32_t depth, uint32_t eliminated, uint32_t cand,
-                                            uint32_t tot, uint32_t cs, int32_t child, bool has_obs, int big_sel) {
+                                            uint32_t tot, uint32_t cs, int32_t child, uint32_t obs) {
   const bool standing = !(eliminated >> cand & 1u);
   if (standing) atomicAdd(&ws.tally[cand], tot);
-  const bool cont = cs > 0u || (has_obs && child >= 0);
+  const bool cont = cs > 0u || (obs > 0u && child >= 0);
   if (!cont) return;  // these ballots end with `cand`: they exhaust when it is eliminated
   DItem ch;
-  ch.prefix.w[0] = 0;
+  ch.prefix.w[0] = cs + (child >= 0 ? obs : 0u);  // sampled ballots that go on + observed ones below
   ch.node_key = child_node_key(x.node_key, cand);
   ch.count = cs;
   ch.node = child;
   ch.used = x.used | (1u << cand);
   ch.pad_ = depth + 1u;
-  if (!standing) {  // its candidate is already out: split it in this round as well
-    enqueue_node(a, ws, sc, cp, ch, big_sel);
+  if (!standing) {  // its candidate is already out: it waits to be split
+    enqueue_node(a, ws, sc, cp, ch);
     return;
   }
   // park it under `cand`: reuse a freed pool slot if there is one, else grow the pool
@@ -132,7 +140,7 @@ static __device__ __noinline__ void route_child(const SimArgs &a, DeferredWarp &
 
 // One lane splits one node with a small sampled count (0..urn_max) and routes its children.
 __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp &ws, const DeferredScratch &sc,
-                                                 const DeferredCaps &cp, const DItem &x, uint32_t eliminated, const RngKey key, int big_sel,
+                                                 const DeferredCaps &cp, const DItem &x, uint32_t eliminated, const RngKey key,
                                                  uint32_t *stat) {
   const uint32_t nc = a.P.nc;
   const uint32_t depth = x.pad_ & 0xFFu;
@@ -157,7 +165,7 @@ __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp 
       const uint32_t obs = a.T.slot_count[nb + slot];
       if (c + obs == 0u) continue;
       route_child(a, ws, sc, cp, x, depth, eliminated, a.T.slot_cand[nb + slot], c + obs, lv.leaf_children ? 0u : c,
-                  a.T.slot_child[nb + slot], obs > 0u, big_sel);
+                  a.T.slot_child[nb + slot], obs);
     }
   } else {
     // prior-only subtree (or sampling with replacement): only the drawn outcomes matter
@@ -176,7 +184,7 @@ __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp 
       if (slot == lv.K) continue;  // the ballots stop here: exhausted
       const uint32_t cand = nb != 0xFFFFFFFFu ? (uint32_t)a.T.slot_cand[nb + slot] : nth_unused(x.used, nc, slot);
       const int32_t child = nb != 0xFFFFFFFFu ? a.T.slot_child[nb + slot] : -1;
-      route_child(a, ws, sc, cp, x, depth, eliminated, cand, c, lv.leaf_children ? 0u : c, child, false, big_sel);
+      route_child(a, ws, sc, cp, x, depth, eliminated, cand, c, lv.leaf_children ? 0u : c, child, 0u);
     }
   }
 }
@@ -185,7 +193,7 @@ __device__ __forceinline__ void split_small_node(const SimArgs &a, DeferredWarp 
 template <bool LOG>
 __device__ void split_big_nodes(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
                                 const DeferredCaps &cp, const DItem *list, uint32_t n_list, uint32_t eliminated, int log_dp_max,
-                                const RngKey key, int big_sel, uint32_t *stat) {
+                                const RngKey key, uint32_t *stat) {
   const int lane = threadIdx.x & 31;
   const uint32_t nc = a.P.nc;
   const uint32_t dp_max = 1u << log_dp_max, stride = 2u * dp_max + 1u;
@@ -219,50 +227,93 @@ __device__ void split_big_nodes(const SimArgs &a, WarpTile<1> &wt, DeferredWarp 
         cand = nth_unused(x.used, nc, slot);
       }
       if (c + obs == 0u) continue;
-      route_child(a, ws, sc, cp, x, depth, eliminated, cand, c + obs, lv.leaf_children ? 0u : c, child, obs > 0u, big_sel);
+      route_child(a, ws, sc, cp, x, depth, eliminated, cand, c + obs, lv.leaf_children ? 0u : c, child, obs);
     }
     __syncwarp();
   }
 }
 
-// Splits everything that is queued, and whatever that enqueues, until nothing is left.
+// Splits every waiting node that holds at least `tau` ballots; lighter ones keep waiting. Children whose candidate
+// is out join the waiting lists (and wait for the next call).
 template <bool LOG>
-__device__ void deferred_drain(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
-                               const DeferredCaps &cp, uint32_t &q_head, uint32_t &hw_queue, uint32_t &hw_big,
-                               uint32_t eliminated, int log_dp_max, const RngKey key, uint32_t *stat) {
+__device__ void deferred_resolve(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
+                                 const DeferredCaps &cp, uint32_t &q_head, uint32_t &hw_queue, uint32_t &hw_big,
+                                 uint32_t eliminated, uint32_t tau, int log_dp_max, const RngKey key, uint32_t *stat) {
   const int lane = threadIdx.x & 31;
-  int sel = 0;  // big[sel] is being filled
-  for (;;) {
-    // small counts: 32 nodes at a time, one lane each; their eliminated-candidate children rejoin the queue
-    for (;;) {
-      __syncwarp();
-      const uint32_t tail = ws.q_tail;
-      if (q_head >= tail || ws.overflow) break;
-      hw_queue = max(hw_queue, tail - q_head);
-      const uint32_t i = q_head + lane;
+  __syncwarp();
+  // small counts: one turn of the circular queue, 32 nodes at a time, one lane each
+  const uint32_t n_small = ws.q_tail - q_head;
+  hw_queue = max(hw_queue, n_small);
+  if (n_small && ws.small_mass_max >= tau) {
+    for (uint32_t done = 0; done < n_small && !ws.overflow; done += 32u) {
+      const uint32_t m = min(32u, n_small - done);
       DItem x;
-      if (i < tail) x = sc.queue[i % cp.queue];
-      q_head = min(q_head + 32u, tail);
+      if ((uint32_t)lane < m) x = sc.queue[(q_head + lane) % cp.queue];
+      q_head += m;
       __syncwarp();  // the batch has been read: its queue slots may be reused from here on
       if (lane == 0) ws.q_head = q_head;
       __syncwarp();
-      if (i < tail) split_small_node(a, ws, sc, cp, x, eliminated, key, sel, stat);
+      if ((uint32_t)lane < m) {
+        const uint32_t mass = node_mass(x);
+        if (mass >= tau) {
+          atomicSub(&ws.unresolved, mass);
+          split_small_node(a, ws, sc, cp, x, eliminated, key, stat);
+        } else {  // back to the end of the queue
+          const uint32_t q = coalesced_reserve(&ws.q_tail);
+          if (q - ws.q_head < cp.queue) sc.queue[q % cp.queue] = x;
+          else ws.overflow = 1;
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    const uint32_t n_big = min(ws.big_tail, cp.big);
-    if (n_big == 0 || ws.overflow) break;
-    hw_big = max(hw_big, n_big);
-    __syncwarp();
-    if (lane == 0) ws.big_tail = 0;
-    __syncwarp();
-    split_big_nodes<LOG>(a, wt, ws, sc, cp, sc.big[sel], n_big, eliminated, log_dp_max, key, sel ^ 1, stat);
-    sel ^= 1;
   }
+  __syncwarp();
+  // big counts: the heavy ones move to big[1] and go through the tile, the rest are compacted in big[0]
+  const uint32_t n_big = min(ws.big_tail, cp.big);
+  hw_big = max(hw_big, n_big);
+  if (n_big == 0u || ws.overflow) return;
+  uint32_t n_keep = 0, n_work = 0, work_mass = 0;
+  for (uint32_t start = 0; start < n_big; start += 32u) {
+    const uint32_t i = start + lane;
+    DItem x;
+    bool heavy = false, keep = false;
+    if (i < n_big) {
+      x = sc.big[0][i];
+      heavy = node_mass(x) >= tau;
+      keep = !heavy;
+    }
+    const uint32_t hm = __ballot_sync(0xffffffffu, heavy), km = __ballot_sync(0xffffffffu, keep);
+    const uint32_t below = (1u << lane) - 1u;
+    __syncwarp();  // every lane has read its node before any slot of big[0] is rewritten
+    if (heavy) {
+      sc.big[1][n_work + __popc(hm & below)] = x;
+      work_mass += node_mass(x);
+    }
+    if (keep) sc.big[0][n_keep + __popc(km & below)] = x;
+    n_work += __popc(hm);
+    n_keep += __popc(km);
+  }
+  work_mass = __reduce_add_sync(0xffffffffu, work_mass);
+  __syncwarp();
+  if (lane == 0) {
+    ws.big_tail = n_keep;
+    ws.unresolved -= work_mass;
+  }
+  __syncwarp();
+  if (n_work) split_big_nodes<LOG>(a, wt, ws, sc, cp, sc.big[1], n_work, eliminated, log_dp_max, key, stat);
   __syncwarp();
 }
 
 // One election in the arena (sc, cp). Returns false if the arena was too small (nothing is recorded then).
 // On success *eliminated_out / *order_out / *ties_out describe the outcome (lane r holds round r's loser).
+//
+// Nodes released by an elimination are not split as they appear: they wait, their ballots counted in
+// ws.unresolved, and a round is decided as soon as its outcome cannot depend on where those ballots go. They can
+// only add to tallies, so the weakest candidate stays weakest if its tally plus all unresolved ballots is still
+// below every other tally, and a leader keeps a majority if it has one with all of them counted against it. While
+// neither holds, the waiting nodes heavy enough to matter are split (deferred_resolve) and the test is repeated.
+// Every split is a pure function of the node, so which ones are carried out changes no outcome: elimination
+// orders and winners are those of the eager evaluation (simulate_kernel).
 template <bool LOG>
 __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
                                   const DeferredCaps &cp, const RngKey key, uint32_t n_rounds, int log_dp_max,
@@ -273,7 +324,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
   ws.tally[lane] = 0;
   if (lane == 0) {
     DItem root;
-    root.prefix.w[0] = 0;
+    root.prefix.w[0] = max(a.n_sample, 1u);  // any positive number: nothing can be decided before the root is split
     root.node_key = kRootNodeKey;
     root.count = a.n_sample;
     root.node = 0;
@@ -285,39 +336,55 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
     ws.q_tail = 0;
     ws.q_head = 0;
     ws.big_tail = 0;
+    ws.unresolved = (uint32_t)root.prefix.w[0];
+    ws.small_mass_max = 0;
     if (a.n_sample > a.urn_max) {
       sc.big[0][0] = root;
       ws.big_tail = 1;
     } else {
       sc.queue[0] = root;
       ws.q_tail = 1;
+      ws.small_mass_max = (uint32_t)root.prefix.w[0];
     }
   }
   __syncwarp();
   uint32_t eliminated = 0, tie_rounds = 0, my_order = 0xFFu, q_head = 0, hw_queue = 0, hw_big = 0;
   const bool early_stop = a.n_winners == 1u && a.elim_orders == nullptr;
 
-  // Pass -1 splits the root; pass r >= 0 eliminates a candidate, then splits what was parked under it.
-  for (int pass = -1; pass < (int)n_rounds && !ws.overflow; ++pass) {
-    if (pass >= 0) {
-    const uint32_t round = (uint32_t)pass;
+  for (uint32_t round = 0; round < n_rounds && !ws.overflow; ++round) {
     // candidates with the minimal tally among those standing (irv_ballot.cpp:88-98), one lane each
     const bool standing = lane < (int)nc && !(eliminated >> lane & 1u);
-    if (early_stop) {
-      // A candidate holding more than half of the ballots still in play can never have the minimal tally
-      // again (tallies only grow, ballots in play only shrink), so it is the winner: stop here.
+    uint32_t mn, tied, ntied;
+    bool won = false;
+    for (;;) {
+      __syncwarp();
+      const uint32_t u = ws.unresolved;
       const uint32_t mine = standing ? ws.tally[lane] : 0u;
       const uint32_t total = __reduce_add_sync(0xffffffffu, mine), top = __reduce_max_sync(0xffffffffu, mine);
-      if (top > total - top) {
+      const uint32_t t = standing ? mine : 0xFFFFFFFFu;
+      mn = __reduce_min_sync(0xffffffffu, t);
+      tied = __ballot_sync(0xffffffffu, standing && t == mn);
+      ntied = (uint32_t)__popc(tied);
+      const uint32_t second = ntied > 1u ? mn : __reduce_min_sync(0xffffffffu, (standing && t != mn) ? t : 0xFFFFFFFFu);
+      // A candidate holding more than half of the ballots still in play can never have the minimal tally
+      // again (tallies only grow, ballots in play only shrink), so it is the winner: stop here.
+      const uint32_t lead = top > total - top ? top - (total - top) : 0u;  // its margin over everybody else together
+      if (early_stop && lead > u) {
         const uint32_t who = __ballot_sync(0xffffffffu, standing && mine == top);
         eliminated = ~who & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+        won = true;
         break;
       }
+      const uint32_t gap = second - mn;  // 0 when tied
+      if (u == 0u || gap > u) break;     // the weakest candidate is known
+      if (ws.overflow) break;
+      // Split what can matter: with n nodes waiting, those lighter than need / (2 n) hold less than need / 2 together.
+      const uint32_t need = early_stop ? max(gap, lead) : gap;
+      const uint32_t n_wait = (ws.q_tail - q_head) + ws.big_tail;
+      const uint32_t tau = need / (2u * max(n_wait, 1u)) + 1u;
+      deferred_resolve<LOG>(a, wt, ws, sc, cp, q_head, hw_queue, hw_big, eliminated, tau, log_dp_max, key, stat);
     }
-    const uint32_t t = standing ? ws.tally[lane] : 0xFFFFFFFFu;
-    const uint32_t mn = __reduce_min_sync(0xffffffffu, t);
-    uint32_t tied = __ballot_sync(0xffffffffu, standing && t == mn);
-    const uint32_t ntied = (uint32_t)__popc(tied);
+    if (won || ws.overflow) break;
     if (ntied > 1u) {  // uniform among the tied, ascending index (irv_ballot.cpp:100-102)
       U4 r = node_random(key, 0ull, kStreamTie, round);
       const uint32_t pick = uniform_below(r.x, ntied);
@@ -332,7 +399,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
     // the loser's ballots are not redistributed. The reference does redistribute them (irv_ballot.cpp:109-133) -
     // typically the runner-up's whole subtree - without any effect on its output.
     if (round + 1u == n_rounds) continue;
-    // queue the nodes parked under the eliminated candidate: scan the holder bytes 16 per lane
+    // release the nodes parked under the eliminated candidate: scan the holder bytes 16 per lane
     if (lane == 0 && ws.n_free < 0) ws.n_free = 0;
     __syncwarp();
     const uint32_t np = min(ws.n_pool, cp.pool);
@@ -356,19 +423,17 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
         if (j >= np) break;
         sc.holder[j] = 0xFF;
         const DItem x = sc.pool[j];
-        enqueue_node(a, ws, sc, cp, x, 0);
+        enqueue_node(a, ws, sc, cp, x);
         const uint32_t f = coalesced_reserve(reinterpret_cast<uint32_t *>(&ws.n_free));
         sc.free_list[f] = j;
       }
     }
     __syncwarp();
-    }  // pass >= 0
-    deferred_drain<LOG>(a, wt, ws, sc, cp, q_head, hw_queue, hw_big, eliminated, log_dp_max, key, stat);
   }
   __syncwarp();
   usage[0] = max(usage[0], min(ws.n_pool, 0x7FFFFFFFu));
-  usage[1] = max(usage[1], hw_queue);
-  usage[2] = max(usage[2], hw_big);
+  usage[1] = max(usage[1], max(hw_queue, ws.q_tail - q_head));
+  usage[2] = max(usage[2], max(hw_big, min(ws.big_tail, cp.big)));
   eliminated_out = eliminated;
   order_out = my_order;
   ties_out = tie_rounds;

@@ -41,18 +41,58 @@ struct LaneShared {
   uint32_t tally[kMaxCandidates][BLOCK];  // [candidate][thread]: a warp reading one candidate hits 32 banks
 };
 
+// Waiting nodes: those holding more than urn_max ballots in a max-heap keyed by the number of ballots (so that the
+// node that matters most to an undecided round is split first), the rest in a circular queue.
 __device__ __forceinline__ void lane_enqueue(const SimArgs &a, const DeferredScratch &sc, const DeferredCaps &cp,
                                              LaneState &st, const DItem &ch) {
-  if (ch.count > a.urn_max) {
-    if (st.n_big < cp.big) sc.big[0][st.n_big++] = ch;
-    else st.overflow = true;
+  const uint32_t m = lane_mass(ch);
+  st.unresolved += m;
+  if (m > a.urn_max) {
+    if (st.n_big < cp.big) {
+      DItem *heap = sc.big[0];
+      uint32_t i = st.n_big++;
+      while (i > 0u) {
+        const uint32_t parent = (i - 1u) >> 1;
+        if (lane_mass(heap[parent]) >= m) break;
+        heap[i] = heap[parent];
+        i = parent;
+      }
+      heap[i] = ch;
+    } else {
+      st.overflow = true;
+    }
     st.hw_big = max(st.hw_big, st.n_big);
   } else {
     if (st.q_tail - st.q_head < cp.queue) sc.queue[(st.q_tail++) % cp.queue] = ch;
     else st.overflow = true;
-    st.unresolved += lane_mass(ch);
     st.hw_queue = max(st.hw_queue, st.q_tail - st.q_head);
   }
+}
+
+// Removes and returns the waiting node with the most ballots.
+__device__ __forceinline__ DItem lane_pop_heaviest(const DeferredScratch &sc, LaneState &st) {
+  DItem *heap = sc.big[0];
+  const DItem top = heap[0];
+  const uint32_t n = --st.n_big;
+  if (n) {
+    const DItem last = heap[n];
+    const uint32_t lm = lane_mass(last);
+    uint32_t i = 0;
+    for (;;) {
+      uint32_t c = 2u * i + 1u;
+      if (c >= n) break;
+      uint32_t cm = lane_mass(heap[c]);
+      if (c + 1u < n) {
+        const uint32_t rm = lane_mass(heap[c + 1u]);
+        if (rm > cm) { cm = rm; ++c; }
+      }
+      if (cm <= lm) break;
+      heap[i] = heap[c];
+      i = c;
+    }
+    heap[i] = last;
+  }
+  return top;
 }
 
 // Same contract as route_child (deferred.cuh), for a lane that owns its election.
@@ -258,32 +298,28 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
     st.hw_queue = 0; st.hw_big = 0; st.unresolved = 0; st.overflow = false;
 #pragma unroll 1
     for (uint32_t c = 0; c < nc; ++c) sh.tally[c][tid] = 0;
-    if (active) {
-      DItem root;
-      root.prefix.w[0] = a.n_sample;
-      root.node_key = kRootNodeKey;
-      root.count = a.n_sample;
-      root.node = 0;
-      root.used = 0;
-      root.pad_ = 0;
-      lane_enqueue(a, sc, cp, st, root);
-    }
+    DItem root;
+    root.prefix.w[0] = 0;
+    root.node_key = kRootNodeKey;
+    root.count = a.n_sample;
+    root.node = 0;
+    root.used = 0;
+    root.pad_ = 0;
     bool decided = !active;
-    // Pass -1 splits the root; pass r >= 0 eliminates a candidate, then splits what was parked under it.
-    // Nodes with a small sampled count are NOT split as they appear: they wait in the small-count queue, their
-    // ballots counted in st.unresolved, and a round is decided as soon as its outcome cannot depend on where those
-    // ballots go (they can only add to tallies): the weakest candidate stays weakest if its tally plus all
-    // unresolved ballots is still below every other tally. Only while that is not the case are waiting nodes
-    // split, oldest first. Every split is a pure function of the node, so which of them are carried out changes
-    // no outcome: elimination orders and winners are those of the eager evaluation (deferred_kernel, simulate_kernel).
+    // Pass -1 splits the root; pass r >= 0 eliminates a candidate and releases the nodes parked under it.
+    // Released nodes are NOT split as they appear: they wait (lane_enqueue), their ballots counted in
+    // st.unresolved, and a round is decided as soon as its outcome cannot depend on where those ballots go. They
+    // can only add to tallies, so the weakest candidate stays weakest if its tally plus all unresolved ballots is
+    // still below every other tally (and a leader keeps a majority if it has one counting them all against it).
+    // Only while that is not the case are waiting nodes split, the one with the most ballots first. Every split is
+    // a pure function of the node, so which of them are carried out changes no outcome: elimination orders and
+    // winners are those of the eager evaluation (deferred_kernel, simulate_kernel).
     for (int pass = -1; pass < (int)n_rounds; ++pass) {
       if (pass < 0) {
-        // a root with a small sampled count is split at once (it holds every ballot)
-        const bool small_root = active && st.q_head < st.q_tail;
-        if (small_root) {
-          const DItem x = sc.queue[(st.q_head++) % cp.queue];
-          st.unresolved -= lane_mass(x);
-          lane_split_small<BLOCK>(a, sh, sc, cp, st, x, key, stat);
+        // the root holds every ballot: split at once
+        if (active) {
+          if (a.n_sample > a.urn_max) lane_split_big<BLOCK, LOG>(a, sh, sc, cp, st, root, key, row, stat);
+          else lane_split_small<BLOCK>(a, sh, sc, cp, st, root, key, stat);
         }
       } else {
         const uint32_t round = (uint32_t)pass;
@@ -349,20 +385,12 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
           }
           if (!__any_sync(0xffffffffu, uncertain)) break;
           if (uncertain && !st.overflow) {
-            const DItem x = sc.queue[(st.q_head++) % cp.queue];
+            const DItem x = st.n_big ? lane_pop_heaviest(sc, st) : sc.queue[(st.q_head++) % cp.queue];
             st.unresolved -= lane_mass(x);
-            lane_split_small<BLOCK>(a, sh, sc, cp, st, x, key, stat);
+            if (x.count > a.urn_max) lane_split_big<BLOCK, LOG>(a, sh, sc, cp, st, x, key, row, stat);
+            else lane_split_small<BLOCK>(a, sh, sc, cp, st, x, key, stat);
           }
           if (st.overflow) pending = false;
-        }
-      }
-      // big nodes are always split: one per turn, lanes wait for each other per turn
-      for (;;) {
-        const bool has_big = !decided && !st.overflow && st.n_big > 0;
-        if (!__any_sync(0xffffffffu, has_big)) break;
-        if (has_big) {
-          const DItem x = sc.big[0][--st.n_big];
-          lane_split_big<BLOCK, LOG>(a, sh, sc, cp, st, x, key, row, stat);
         }
       }
     }
