@@ -239,7 +239,10 @@ def main():
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kernel_ev = []
+        total.add_(wins)  # first use of these torch ops loads their kernels: not inside the timed region
+        l2_flush.zero_()
         total.zero_()
+        torch.cuda.synchronize(dev)
         ev0.record(stream)
         step_ev = []
         for i in range(steps):
@@ -270,6 +273,8 @@ def main():
                 "steps": steps, "elections_per_gpu": n_el,
                 "kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in kernel_ev])),
                 "kernel_ms_steps": [round(a.elapsed_time(b), 3) for a, b in kernel_ev], "stats": st,
+                "step_ms_steps": [round(a.elapsed_time(b), 3) for a, b in step_ev],
+                "after_kernel_ms_steps": [round(k[1].elapsed_time(s_[1]), 3) for k, s_ in zip(kernel_ev, step_ev)],
                 "kernel": {0: "simulate_kernel", 1: "deferred_kernel", 2: "lane_kernel"}[st["mode"]]}
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -388,6 +393,7 @@ def main():
                "traffic_source": tr.get("capture") if tr.get("config") == name else None,
                "peak_source": peak_src, "algorithmic_bytes_per_election": bytes_el,
                "kernel_ms_per_launch": m["kernel_ms"], "kernel_ms_steps": m["kernel_ms_steps"],
+               "step_ms_steps": m.get("step_ms_steps"), "after_kernel_ms_steps": m.get("after_kernel_ms_steps"),
                "elections_per_launch": n_el}
         if m["kernel"] != "simulate_kernel":
             eq = b_alg * n_el / secs / 1e9
