@@ -26,7 +26,8 @@ struct LaneState {
   uint32_t n_pool;            // high-water mark of the parked pool
   uint32_t n_free;            // free-list depth
   uint32_t q_head, q_tail;    // circular small-count queue (monotone counters)
-  uint32_t n_big;             // big-count stack depth
+  uint32_t n_big;             // waiting heavy nodes in the heap (beyond the kLaneTop kept apart)
+  uint32_t n_top;             // waiting heavy nodes whose ballot counts sit in shared memory
   uint32_t eliminated;
   uint32_t hw_queue, hw_big;
   uint32_t unresolved;        // ballots (sampled + observed) inside the nodes waiting in the small-count queue
@@ -36,20 +37,34 @@ struct LaneState {
 // A queued or parked node carries the number of ballots inside it in the (otherwise unused) prefix word.
 __device__ __forceinline__ uint32_t lane_mass(const DItem &x) { return (uint32_t)x.prefix.w[0]; }
 
+constexpr uint32_t kLaneTop = 16;  // heavy waiting nodes per election whose ordering never touches global memory
+
 template <int BLOCK>
 struct LaneShared {
   uint32_t tally[kMaxCandidates][BLOCK];  // [candidate][thread]: a warp reading one candidate hits 32 banks
+  uint32_t top_mass[kLaneTop][BLOCK];     // ballots in big[0][i], i < kLaneTop; 0 = slot free
 };
 
-// Waiting nodes: those holding more than urn_max ballots in a max-heap keyed by the number of ballots (so that the
-// node that matters most to an undecided round is split first), the rest in a circular queue.
-__device__ __forceinline__ void lane_enqueue(const SimArgs &a, const DeferredScratch &sc, const DeferredCaps &cp,
-                                             LaneState &st, const DItem &ch) {
+// Waiting nodes: those holding more than urn_max ballots are kept so that the heaviest can be taken first (it is
+// the one that matters most to an undecided round) — the first kLaneTop in fixed slots of big[0] with their
+// ballot counts in shared memory (a light election never has more), the rest in a max-heap behind them; nodes
+// with at most urn_max ballots in a circular queue.
+template <int BLOCK>
+__device__ __forceinline__ void lane_enqueue(const SimArgs &a, LaneShared<BLOCK> &sh, const DeferredScratch &sc,
+                                             const DeferredCaps &cp, LaneState &st, const DItem &ch) {
   const uint32_t m = lane_mass(ch);
   st.unresolved += m;
   if (m > a.urn_max) {
-    if (st.n_big < cp.big) {
-      DItem *heap = sc.big[0];
+    if (st.n_top < kLaneTop && kLaneTop <= cp.big) {
+      uint32_t i = 0;
+#pragma unroll
+      for (uint32_t k = kLaneTop; k-- > 0u;)
+        if (sh.top_mass[k][threadIdx.x] == 0u) i = k;
+      sh.top_mass[i][threadIdx.x] = m;
+      sc.big[0][i] = ch;
+      ++st.n_top;
+    } else if (kLaneTop + st.n_big < cp.big) {
+      DItem *heap = sc.big[0] + kLaneTop;
       uint32_t i = st.n_big++;
       while (i > 0u) {
         const uint32_t parent = (i - 1u) >> 1;
@@ -61,7 +76,7 @@ __device__ __forceinline__ void lane_enqueue(const SimArgs &a, const DeferredScr
     } else {
       st.overflow = true;
     }
-    st.hw_big = max(st.hw_big, st.n_big);
+    st.hw_big = max(st.hw_big, st.n_top + st.n_big);
   } else {
     if (st.q_tail - st.q_head < cp.queue) sc.queue[(st.q_tail++) % cp.queue] = ch;
     else st.overflow = true;
@@ -69,9 +84,23 @@ __device__ __forceinline__ void lane_enqueue(const SimArgs &a, const DeferredScr
   }
 }
 
-// Removes and returns the waiting node with the most ballots.
-__device__ __forceinline__ DItem lane_pop_heaviest(const DeferredScratch &sc, LaneState &st) {
-  DItem *heap = sc.big[0];
+// Removes and returns the waiting node with the most ballots (there is one: n_top + n_big > 0).
+template <int BLOCK>
+__device__ __forceinline__ DItem lane_pop_heaviest(LaneShared<BLOCK> &sh, const DeferredScratch &sc, LaneState &st) {
+  uint32_t best = 0, best_mass = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < kLaneTop; ++k) {
+    const uint32_t m = sh.top_mass[k][threadIdx.x];
+    if (m > best_mass) { best_mass = m; best = k; }
+  }
+  DItem *heap = sc.big[0] + kLaneTop;
+  if (st.n_big == 0u || lane_mass(heap[0]) <= best_mass) {
+    if (best_mass != 0u) {
+      sh.top_mass[best][threadIdx.x] = 0u;
+      --st.n_top;
+      return sc.big[0][best];
+    }
+  }
   const DItem top = heap[0];
   const uint32_t n = --st.n_big;
   if (n) {
@@ -112,13 +141,14 @@ __device__ __forceinline__ void lane_route(const SimArgs &a, LaneShared<BLOCK> &
   ch.used = x.used | (1u << cand);
   ch.pad_ = depth + 1u;
   if (!standing) {
-    lane_enqueue(a, sc, cp, st, ch);
+    lane_enqueue<BLOCK>(a, sh, sc, cp, st, ch);
     return;
   }
+  // park it: fresh pool slots while there are any (no load on the way), then recycled ones
   uint32_t j;
-  if (st.n_free) j = sc.free_list[--st.n_free];
-  else j = st.n_pool++;
-  if (j >= cp.pool) {
+  if (st.n_pool < cp.pool) j = st.n_pool++;
+  else if (st.n_free) j = sc.free_list[--st.n_free];
+  else {
     st.overflow = true;
     return;
   }
@@ -294,7 +324,9 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
     const bool active = e < a.n_elections;
     const RngKey key = election_key(a.seed, a.first_election + e);
     LaneState st;
-    st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.eliminated = 0;
+    st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.n_top = 0; st.eliminated = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kLaneTop; ++k) sh.top_mass[k][tid] = 0;
     st.hw_queue = 0; st.hw_big = 0; st.unresolved = 0; st.overflow = false;
 #pragma unroll 1
     for (uint32_t c = 0; c < nc; ++c) sh.tally[c][tid] = 0;
@@ -376,7 +408,7 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
                     if (j >= np) break;
                     sc.holder[j] = 0xFF;
                     const DItem x = sc.pool[j];
-                    lane_enqueue(a, sc, cp, st, x);
+                    lane_enqueue<BLOCK>(a, sh, sc, cp, st, x);
                     sc.free_list[st.n_free++] = j;
                   }
                 }
@@ -385,7 +417,7 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
           }
           if (!__any_sync(0xffffffffu, uncertain)) break;
           if (uncertain && !st.overflow) {
-            const DItem x = st.n_big ? lane_pop_heaviest(sc, st) : sc.queue[(st.q_head++) % cp.queue];
+            const DItem x = (st.n_top + st.n_big) ? lane_pop_heaviest<BLOCK>(sh, sc, st) : sc.queue[(st.q_head++) % cp.queue];
             st.unresolved -= lane_mass(x);
             if (x.count > a.urn_max) lane_split_big<BLOCK, LOG>(a, sh, sc, cp, st, x, key, row, stat);
             else lane_split_small<BLOCK>(a, sh, sc, cp, st, x, key, stat);
