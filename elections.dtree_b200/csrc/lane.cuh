@@ -37,7 +37,7 @@ struct LaneState {
 // A queued or parked node carries the number of ballots inside it in the (otherwise unused) prefix word.
 __device__ __forceinline__ uint32_t lane_mass(const DItem &x) { return (uint32_t)x.prefix.w[0]; }
 
-constexpr uint32_t kLaneTop = 16;  // heavy waiting nodes per election whose ordering never touches global memory
+constexpr uint32_t kLaneTop = 32;  // heavy waiting nodes per election whose ordering never touches global memory
 
 template <int BLOCK>
 struct LaneShared {

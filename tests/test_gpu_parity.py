@@ -268,13 +268,19 @@ def test_determinism_and_range_splitting(pkg, L):
     (10, 0, 10, 1.0, False, 3000, 100_000, False), (5, 0, 5, 0.0, False, 40, 400, True),
     (8, 7, 7, 1e-4, True, 100, 20_000, False), (20, 0, 20, 1.0, False, 500, 50_000, False),
     (32, 0, 32, 1.0, False, 300, 5000, False), (14, 3, 9, 2.0, True, 200, 3000, True),
-    (2, 0, 2, 1.0, False, 20, 100, False), (3, 0, 2, 0.5, False, 30, 90, False), (3, 1, 3, 1.0, True, 0, 7, False)])
+    (2, 0, 2, 1.0, False, 20, 100, False), (3, 0, 2, 0.5, False, 30, 90, False), (3, 1, 3, 1.0, True, 0, 7, False),
+    # rounds that hinge on a handful of ballots (ties, near-ties): the deferred kernels must resolve exactly as
+    # much of the tree as the outcome needs
+    (6, 0, 6, 1.0, False, 0, 30, False), (7, 0, 7, 0.01, False, 50, 5000, False),
+    (10, 0, 10, 1.0, False, 0, 200_000, False), (12, 0, 12, 1.0, False, 2000, 20_000, True),
+    (8, 0, 8, 0.2, False, 64, 64, False)])
 def test_deferred_equals_materialised(pkg, L, nc, mn, mx, a0, vd, n_obs, n_ballots, replace):
     """mode=1 / mode=2 (expand a node only when IRV looks below it; a warp / a thread per election) and mode=0
     (materialise every ballot, as the reference does) must give the same elimination order for every election and
     the same win counts:
-    both evaluate the same counter-based draws. Includes observed ballots longer than max_depth, n_ballots
-    == n_observed (nothing sampled), an empty tree, a0 = 0 and every key width."""
+    both evaluate the same counter-based draws, and the deferred kernels decide a round as soon as the ballots they have
+    not yet placed cannot change it. Includes observed ballots longer than max_depth, n_ballots == n_observed
+    (nothing sampled), an empty tree, a0 = 0, flat priors (every round close) and every key width."""
     pmf = np.ones(nc + 1)
     pmf[:mn] = 0
     t = pkg.dirichlet_tree(names(pkg, nc), mn, mx, a0, vd, device=0)
