@@ -379,14 +379,16 @@ def main():
         """algorithmic bytes per launch / CUDA-event duration of the launch, against measured HBM copy
         bandwidth. The materialising kernel moves 8(d)'s bytes (B_alg = 4S + 32E + 16R + 8nc). The deferred kernel
         and lane kernels never create most of them, so they are rated on the bytes THEIR algorithm must move (4 B per outcome slot read +
-        a 32 B node record written and read once per node split + 8nc); the 8(d) rate is kept beside it."""
+        every 32 B node record written to or read back from the per-election arena, counted by the kernel, + 8nc, DESIGN.md 5.1);
+        the 8(d) rate is kept beside it."""
         n_el, secs = m["elections_per_gpu"], m["kernel_ms"] / 1e3
         st = m["stats"]
         per_el = max(st["elections"], 1)
         if m["kernel"] == "simulate_kernel":
             bytes_el = b_alg
         else:
-            bytes_el = 4.0 * st["slots"] / per_el + 64.0 * st["items"] / per_el + 8 * nc
+            # 4 B per outcome slot read + every 32 B node record the kernel wrote to / read back from its arena + 8nc
+            bytes_el = 4.0 * st["slots"] / per_el + 32.0 * (st["entries"] + st["irv_rereads"]) / per_el + 8 * nc
         ach = bytes_el * n_el / secs / 1e9
         tr = traffic_tab.get(m["kernel"], {})
         out = {"kernel": m["kernel"], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

@@ -47,6 +47,7 @@ struct DeferredWarp {
   uint32_t overflow;
   uint32_t unresolved;      // ballots (sampled + observed) inside the waiting nodes
   uint32_t small_mass_max;  // largest number of ballots any node in the small-count queue has had
+  uint32_t rec_w;           // node records written by route_child (traffic accounting)
 };
 
 // A waiting or parked node carries the number of ballots inside it in the (otherwise unused) prefix word.
@@ -105,6 +106,7 @@ static __device__ __noinline__ void route_child(const SimArgs &a, DeferredWarp &
   if (standing) atomicAdd(&ws.tally[cand], tot);
   const bool cont = cs > 0u || (obs > 0u && child >= 0);
   if (!cont) return;  // these ballots end with `cand`: they exhaust when it is eliminated
+  atomicAdd(&ws.rec_w, 1u);
   DItem ch;
   ch.prefix.w[0] = cs + (child >= 0 ? obs : 0u);  // sampled ballots that go on + observed ones below
   ch.node_key = child_node_key(x.node_key, cand);
@@ -255,10 +257,12 @@ __device__ void deferred_resolve(const SimArgs &a, WarpTile<1> &wt, DeferredWarp
       __syncwarp();
       if ((uint32_t)lane < m) {
         const uint32_t mass = node_mass(x);
+        stat[kStatRereads] += 1;
         if (mass >= tau) {
           atomicSub(&ws.unresolved, mass);
           split_small_node(a, ws, sc, cp, x, eliminated, key, stat);
         } else {  // back to the end of the queue
+          stat[kStatEntries] += 1;
           const uint32_t q = coalesced_reserve(&ws.q_tail);
           if (q - ws.q_head < cp.queue) sc.queue[q % cp.queue] = x;
           else ws.overflow = 1;
@@ -281,6 +285,8 @@ __device__ void deferred_resolve(const SimArgs &a, WarpTile<1> &wt, DeferredWarp
       x = sc.big[0][i];
       heavy = node_mass(x) >= tau;
       keep = !heavy;
+      stat[kStatRereads] += 1;  // read here, written to its new place below
+      stat[kStatEntries] += 1;
     }
     const uint32_t hm = __ballot_sync(0xffffffffu, heavy), km = __ballot_sync(0xffffffffu, keep);
     const uint32_t below = (1u << lane) - 1u;
@@ -338,6 +344,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
     ws.big_tail = 0;
     ws.unresolved = (uint32_t)root.prefix.w[0];
     ws.small_mass_max = 0;
+    ws.rec_w = 1;
     if (a.n_sample > a.urn_max) {
       sc.big[0][0] = root;
       ws.big_tail = 1;
@@ -423,6 +430,8 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
         if (j >= np) break;
         sc.holder[j] = 0xFF;
         const DItem x = sc.pool[j];
+        stat[kStatRereads] += 1;
+        stat[kStatEntries] += 1;
         enqueue_node(a, ws, sc, cp, x);
         const uint32_t f = coalesced_reserve(reinterpret_cast<uint32_t *>(&ws.n_free));
         sc.free_list[f] = j;
@@ -431,6 +440,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
     __syncwarp();
   }
   __syncwarp();
+  if (lane == 0) stat[kStatEntries] += ws.rec_w;
   usage[0] = max(usage[0], min(ws.n_pool, 0x7FFFFFFFu));
   usage[1] = max(usage[1], max(hw_queue, ws.q_tail - q_head));
   usage[2] = max(usage[2], max(hw_big, min(ws.big_tail, cp.big)));

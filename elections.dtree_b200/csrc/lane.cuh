@@ -30,7 +30,8 @@ struct LaneState {
   uint32_t n_top;             // waiting heavy nodes whose ballot counts sit in shared memory
   uint32_t eliminated;
   uint32_t hw_queue, hw_big;
-  uint32_t unresolved;        // ballots (sampled + observed) inside the nodes waiting in the small-count queue
+  uint32_t unresolved;        // ballots (sampled + observed) inside the waiting nodes
+  uint32_t rec_w, rec_r;      // 32-byte node records written to / read back from the arena (traffic accounting)
   bool overflow;
 };
 
@@ -54,6 +55,7 @@ __device__ __forceinline__ void lane_enqueue(const SimArgs &a, LaneShared<BLOCK>
                                              const DeferredCaps &cp, LaneState &st, const DItem &ch) {
   const uint32_t m = lane_mass(ch);
   st.unresolved += m;
+  ++st.rec_w;
   if (m > a.urn_max) {
     if (st.n_top < kLaneTop && kLaneTop <= cp.big) {
       uint32_t i = 0;
@@ -154,6 +156,7 @@ __device__ __forceinline__ void lane_route(const SimArgs &a, LaneShared<BLOCK> &
   }
   sc.pool[j] = ch;
   sc.holder[j] = (uint8_t)cand;
+  ++st.rec_w;
 }
 
 // Split of a node with a small sampled count (0..urn_max): split_small_node of deferred.cuh without the atomics.
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
     const bool active = e < a.n_elections;
     const RngKey key = election_key(a.seed, a.first_election + e);
     LaneState st;
-    st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.n_top = 0; st.eliminated = 0;
+    st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.n_top = 0; st.eliminated = 0; st.rec_w = 0; st.rec_r = 0;
 #pragma unroll
     for (uint32_t k = 0; k < kLaneTop; ++k) sh.top_mass[k][tid] = 0;
     st.hw_queue = 0; st.hw_big = 0; st.unresolved = 0; st.overflow = false;
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
                     if (j >= np) break;
                     sc.holder[j] = 0xFF;
                     const DItem x = sc.pool[j];
+                    ++st.rec_r;
                     lane_enqueue<BLOCK>(a, sh, sc, cp, st, x);
                     sc.free_list[st.n_free++] = j;
                   }
@@ -419,6 +423,7 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
           if (uncertain && !st.overflow) {
             const DItem x = (st.n_top + st.n_big) ? lane_pop_heaviest<BLOCK>(sh, sc, st) : sc.queue[(st.q_head++) % cp.queue];
             st.unresolved -= lane_mass(x);
+            ++st.rec_r;
             if (x.count > a.urn_max) lane_split_big<BLOCK, LOG>(a, sh, sc, cp, st, x, key, row, stat);
             else lane_split_small<BLOCK>(a, sh, sc, cp, st, x, key, stat);
           }
@@ -427,6 +432,8 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
       }
     }
     if (active) {
+      stat[kStatEntries] += st.rec_w;
+      stat[kStatRereads] += st.rec_r;
       usage[0] = max(usage[0], st.n_pool);
       usage[1] = max(usage[1], st.hw_queue);
       usage[2] = max(usage[2], st.hw_big);

@@ -189,8 +189,10 @@ int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user
  * Returns DTREE_ERR_ARG for an unknown key. */
 int dtree_set_tuning(dtree_t *t, const char *key, int64_t value);
 /* Statistics of the last sampling call on this handle:
- *  [0] kernel launches, [1] elections simulated, [2] sampled entries written, [3] frontier items
- *  processed, [4] Gamma variates drawn, [5] binomial variates drawn, [6] IRV entry re-reads,
+ *  [0] kernel launches, [1] elections simulated, [2] sampled entries written (mode 0) / 32-byte node records
+ *  written to the arenas (modes 1, 2), [3] frontier items
+ *  processed, [4] Gamma variates drawn, [5] binomial variates drawn, [6] IRV entry re-reads (mode 0) / node
+ *  records read back (modes 1, 2),
  *  [7] device bytes of scratch, [8] H2D bytes, [9] D2H bytes, [10] outcome slots read,
  *  [11] nodes split by the urn shortcut, [12] mode used, [13] elections re-run in a worst-case arena,
  *  [14] kernel launches of the last device tree build. */
