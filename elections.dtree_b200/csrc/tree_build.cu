@@ -12,9 +12,9 @@ void DeviceTreeStore::release_all() {
   node_base.release(); node_total.release(); slot_count.release(); obs_cnt.release(); obs_tally0.release();
   slot_child.release(); slot_cand.release(); obs_first.release(); obs_key.release();
   log_prefs.release(); log_slots.release(); log_off.release();
-  node_key.release(); cursor.release(); block_sums.release();
-  if (h_total) cudaFreeHost(h_total);
-  h_total = nullptr;
+  node_key.release(); cursor.release(); block_sums.release(); level_tab.release();
+  if (h_tab) cudaFreeHost(h_tab);
+  h_tab = nullptr;
   n_nodes = n_slots = n_obs = 0;
   log_ballots = log_bytes = 0;
 }
@@ -25,6 +25,10 @@ constexpr int kScanBlock = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanBlock * kScanItems;
 constexpr uint32_t kDone = 0xFFFFFFFFu;
+// Level table (device memory, so that no level has to wait for the host): row d = {first node, nodes, first slot, -}
+// of depth d; row kTotRow = {nodes, slots, observed entries, -} of the whole tree.
+constexpr int kTotRow = kMaxCandidates + 1;
+constexpr int kTabWords = 4 * (kMaxCandidates + 2);
 
 struct TreePtrs {
   uint32_t *node_base, *node_total, *slot_count;
@@ -55,8 +59,9 @@ __global__ void slot_sequences_kernel(const uint8_t *__restrict__ prefs, const u
   }
 }
 
-__global__ void init_root_kernel(TreePtrs T, uint32_t *obs_tally0, uint32_t nc, int W) {
+__global__ void init_root_kernel(TreePtrs T, uint32_t *obs_tally0, uint32_t *tab, uint32_t nc, int W) {
   const uint32_t j = threadIdx.x;
+  for (uint32_t k = j; k < (uint32_t)kTabWords; k += blockDim.x) tab[k] = 0;
   if (j <= nc) {
     T.slot_count[j] = 0;
     T.slot_child[j] = -1;
@@ -64,9 +69,13 @@ __global__ void init_root_kernel(TreePtrs T, uint32_t *obs_tally0, uint32_t nc, 
   }
   if (j < (uint32_t)kMaxCandidates) obs_tally0[j] = 0;
   if (j < (uint32_t)W) T.node_key[j] = 0;
+  __syncthreads();
   if (j == 0) {
     T.node_base[0] = 0;
     T.node_base[1] = nc + 1;
+    tab[1] = 1;  // depth 0: node 0, one node, slots from 0
+    tab[4 * kTotRow + 0] = 1;
+    tab[4 * kTotRow + 1] = nc + 1;
   }
 }
 
@@ -103,9 +112,10 @@ __global__ void count_level_kernel(TreePtrs T, const uint64_t *__restrict__ off,
 // with a count.
 struct LevelFlag {
   const uint32_t *slot_count;
-  uint32_t slot_lo, per_node;  // per_node = K + 1
+  const uint32_t *row;  // the level's row of the table
+  uint32_t per_node;    // K + 1
   __device__ uint32_t operator()(uint32_t i) const {
-    return ((i % per_node) != per_node - 1u && slot_count[slot_lo + i] > 0u) ? 1u : 0u;
+    return ((i % per_node) != per_node - 1u && slot_count[row[2] + i] > 0u) ? 1u : 0u;
   }
 };
 
@@ -144,8 +154,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
   return before + x - v;
 }
 
+// The number of elements of a scan is count[0] * mul, read on the device; blocks beyond it have nothing to do.
 template <typename F>
-__global__ void __launch_bounds__(kScanBlock) tile_sums_kernel(F f, uint32_t n, uint32_t *__restrict__ block_sums) {
+__global__ void __launch_bounds__(kScanBlock)
+    tile_sums_kernel(F f, const uint32_t *__restrict__ count, uint32_t mul, uint32_t *__restrict__ block_sums) {
+  const uint32_t n = count[0] * mul;
+  if (blockIdx.x * (uint32_t)kScanTile >= n) return;
   const uint32_t first = blockIdx.x * (uint32_t)kScanTile + threadIdx.x * (uint32_t)kScanItems;
   uint32_t s = 0;
 #pragma unroll
@@ -156,9 +170,14 @@ __global__ void __launch_bounds__(kScanBlock) tile_sums_kernel(F f, uint32_t n, 
   if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-// Exclusive scan of the tile sums in place (one block), total to mapped host memory.
-__global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(uint32_t *__restrict__ block_sums, uint32_t nb,
-                                                               uint32_t *__restrict__ total_out) {
+// Exclusive scan of the tile sums in place (one block). The total goes into the table: for a level (depth >= 0)
+// it is the number of nodes of the next depth, whose row and the tree totals are filled in; for the observed
+// entries (depth < 0) it is their number.
+__global__ void __launch_bounds__(kScanBlock)
+    scan_sums_kernel(uint32_t *__restrict__ block_sums, const uint32_t *count, uint32_t mul, uint32_t *tab, int depth,
+                     uint32_t per_node) {
+  const uint32_t n = count[0] * mul;
+  const uint32_t nb = (n + kScanTile - 1) / kScanTile;
   uint32_t carry = 0;
   for (uint32_t start = 0; start < nb; start += kScanBlock) {
     const uint32_t i = start + threadIdx.x;
@@ -168,15 +187,32 @@ __global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(uint32_t *__restr
     if (i < nb) block_sums[i] = carry + ex;
     carry += total;
   }
-  if (threadIdx.x == 0) *total_out = carry;
+  if (threadIdx.x == 0) {
+    uint32_t *tot = tab + 4 * kTotRow;
+    if (depth >= 0) {
+      const uint32_t *row = tab + 4 * depth;
+      uint32_t *next = tab + 4 * (depth + 1);
+      next[0] = row[0] + row[1];
+      next[1] = carry;
+      next[2] = row[2] + row[1] * per_node;
+      tot[0] = next[0] + carry;
+      tot[1] = next[2] + carry * (per_node - 1u);  // a child has one slot less than its parent
+    } else {
+      tot[2] = carry;
+    }
+  }
 }
 
 // Numbers the children of a level and initialises them: slots, candidates (the parent's order with the
 // taken candidate swapped to the front, irv_node.cpp:219), prefix key.
 __global__ void __launch_bounds__(kScanBlock)
-    create_children_kernel(TreePtrs T, LevelFlag f, uint32_t n, const uint32_t *__restrict__ block_sums,
-                           uint32_t level_first_node, uint32_t first_new_node, uint32_t new_slot_base, uint32_t n_new,
+    create_children_kernel(TreePtrs T, LevelFlag f, const uint32_t *__restrict__ tab, const uint32_t *__restrict__ block_sums,
                            uint32_t depth, int W) {
+  const uint32_t *row = tab + 4 * depth, *next = row + 4;
+  const uint32_t n = row[1] * f.per_node, level_first_node = row[0];
+  const uint32_t first_new_node = next[0], n_new = next[1], new_slot_base = next[2];
+  if (blockIdx.x == 0 && threadIdx.x == 0) T.node_base[first_new_node + n_new] = new_slot_base + n_new * (f.per_node - 1u);
+  if (blockIdx.x * (uint32_t)kScanTile >= n) return;
   const uint32_t first = blockIdx.x * (uint32_t)kScanTile + threadIdx.x * (uint32_t)kScanItems;
   uint32_t flags = 0, s = 0;
 #pragma unroll
@@ -191,7 +227,7 @@ __global__ void __launch_bounds__(kScanBlock)
   for (int k = 0; k < kScanItems; ++k) {
     if (!(flags >> k & 1u)) continue;
     const uint32_t i = first + k, pn = i / f.per_node, j = i % f.per_node;
-    const uint32_t slot = f.slot_lo + i, pbase = f.slot_lo + pn * f.per_node;
+    const uint32_t slot = row[2] + i, pbase = row[2] + pn * f.per_node;
     const uint32_t child = first_new_node + rank, cbase = new_slot_base + rank * K;
     ++rank;
     T.slot_child[slot] = (int32_t)child;
@@ -212,12 +248,11 @@ __global__ void __launch_bounds__(kScanBlock)
       T.node_key[(size_t)child * W + w] = key;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) T.node_base[first_new_node + n_new] = new_slot_base + n_new * K;
 }
 
-__global__ void node_totals_kernel(TreePtrs T, uint32_t n_nodes) {
+__global__ void node_totals_kernel(TreePtrs T, const uint32_t *__restrict__ tab) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_nodes) return;
+  if (i >= tab[4 * kTotRow]) return;
   const uint32_t base = T.node_base[i], K = T.node_base[i + 1] - base - 1u;
   uint32_t s = 0;
   for (uint32_t j = 0; j < K; ++j) s += T.slot_count[base + j];
@@ -248,8 +283,10 @@ __device__ void write_observed(const TreePtrs &T, const ObsOut &O, uint32_t at, 
 }
 
 __global__ void __launch_bounds__(kScanBlock)
-    write_observed_kernel(TreePtrs T, ObservedFlag f, uint32_t n_nodes, const uint32_t *__restrict__ block_sums, ObsOut O,
-                          uint32_t nc, int W) {
+    write_observed_kernel(TreePtrs T, ObservedFlag f, const uint32_t *__restrict__ tab, const uint32_t *__restrict__ block_sums,
+                          ObsOut O, uint32_t nc, int W) {
+  const uint32_t n_nodes = tab[4 * kTotRow];
+  if (blockIdx.x * (uint32_t)kScanTile >= n_nodes) return;
   const uint32_t first = blockIdx.x * (uint32_t)kScanTile + threadIdx.x * (uint32_t)kScanItems;
   uint32_t s = 0;
 #pragma unroll
@@ -298,15 +335,19 @@ cudaError_t grow_slots(DeviceTreeStore &S, size_t slots, size_t keep, cudaStream
 }  // namespace
 
 cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t *h_prefs, const uint64_t *h_offsets,
-                                 uint64_t n_ballots, cudaStream_t stream, BuildStats *stats, bool *too_big) {
+                                 uint64_t n_ballots, cudaStream_t stream, BuildStats *stats, bool *too_big,
+                                 uint64_t bound_budget_bytes) {
   const int W = key_words_for(nc);
   BuildStats st;
   if (too_big) *too_big = false;
-  if (!S.h_total) {
-    BUILD_TRY(cudaHostAlloc((void **)&S.h_total, 2 * sizeof(uint32_t), cudaHostAllocMapped));
-  }
-  uint32_t *d_total = nullptr;
-  BUILD_TRY(cudaHostGetDevicePointer((void **)&d_total, S.h_total, 0));
+  if (!S.h_tab) BUILD_TRY(cudaHostAlloc((void **)&S.h_tab, kTabWords * sizeof(uint32_t), cudaHostAllocDefault));
+  BUILD_TRY(S.level_tab.reserve(kTabWords));
+  uint32_t *tab = S.level_tab.p;
+  auto read_table = [&]() -> cudaError_t {  // the one kind of host round trip of a build
+    BUILD_TRY(cudaMemcpyAsync(S.h_tab, tab, kTabWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    ++st.host_syncs;
+    return cudaStreamSynchronize(stream);
+  };
 
   // 1. append the new part of the ballot log and compute its slot sequences
   if (n_ballots < S.log_ballots) S.log_ballots = S.log_bytes = 0;  // the log was reset
@@ -328,82 +369,106 @@ cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t 
     S.log_bytes = bytes;
   }
 
-  // 2. root
-  size_t nodes_guess = std::max<size_t>({(size_t)S.n_nodes + S.n_nodes / 4, (size_t)std::min<uint64_t>(n_ballots, 1u << 24), 64});
-  BUILD_TRY(grow_nodes(S, nodes_guess, 0, W, stream));
-  BUILD_TRY(grow_slots(S, std::max<size_t>((size_t)S.n_slots + S.n_slots / 4, nodes_guess * 4 + nc + 1), 0, stream));
+  // 2. a priori bounds: depth d + 1 has at most min(#ballots, nodes(d) * children) nodes
+  uint64_t ub_nodes[kMaxCandidates + 1] = {0};
+  ub_nodes[0] = 1;
+  uint64_t ub_total = 1, ub_slots = nc + 1;
+  for (uint32_t d = 0; nc - d > 2; ++d) {
+    ub_nodes[d + 1] = std::min<uint64_t>(n_ballots, ub_nodes[d] * (nc - d));
+    ub_total += ub_nodes[d + 1];
+    ub_slots += ub_nodes[d + 1] * (nc - d);  // a node of depth d + 1 has nc - d - 1 children + the stop slot
+  }
+  const uint64_t ub_bytes = ub_total * (8 + 8ull * W) + ub_slots * 9 + n_ballots * (8ull * W + 5);
+  const bool bounded = ub_bytes <= bound_budget_bytes && ub_slots < 0xFFFFFFF0ull;
+
+  // 3. root
+  if (bounded) {
+    BUILD_TRY(grow_nodes(S, ub_total, 0, W, stream));
+    BUILD_TRY(grow_slots(S, ub_slots, 0, stream));
+    BUILD_TRY(S.node_total.grow(ub_total, 0, stream));
+  } else {
+    size_t guess = std::max<size_t>({(size_t)S.n_nodes + S.n_nodes / 4, (size_t)std::min<uint64_t>(n_ballots, 1u << 24), 64});
+    BUILD_TRY(grow_nodes(S, guess, 0, W, stream));
+    BUILD_TRY(grow_slots(S, std::max<size_t>((size_t)S.n_slots + S.n_slots / 4, guess * 4 + nc + 1), 0, stream));
+  }
   BUILD_TRY(S.obs_tally0.reserve(kMaxCandidates));
-  BUILD_TRY(S.cursor.reserve(std::max<uint64_t>(n_ballots, 1)));
-  init_root_kernel<<<1, 64, 0, stream>>>(ptrs(S), S.obs_tally0.p, nc, W);
+  BUILD_TRY(S.cursor.grow(std::max<uint64_t>(n_ballots, 1), 0, stream));
+  init_root_kernel<<<1, 64, 0, stream>>>(ptrs(S), S.obs_tally0.p, tab, nc, W);
   ++st.launches;
 
-  // 3. one level at a time
-  uint32_t n_nodes = 1, n_slots = nc + 1, level_first = 0, level_nodes = 1;
-  S.level_first[0] = 0;
-  uint32_t depth = 0;
+  // 4. one level at a time
+  uint32_t n_nodes = 1, n_slots = nc + 1;  // exact path: what the arrays hold so far
   const int ballot_grid = (int)((n_ballots + 255) / 256);
-  for (;; ++depth) {
+  for (uint32_t depth = 0;; ++depth) {
     const uint32_t K = nc - depth;
     if (n_ballots > 0) {
       count_level_kernel<<<ballot_grid, 256, 0, stream>>>(ptrs(S), S.log_off.p, S.log_slots.p, S.cursor.p, n_ballots, nc, depth);
       ++st.launches;
     }
     if (K <= 2 || n_ballots == 0) break;  // irv_node.cpp:210: a node with two candidates left has no children
-    const uint32_t slot_lo = n_slots - level_nodes * (K + 1), n_level_slots = level_nodes * (K + 1);
-    const uint32_t nb = (n_level_slots + kScanTile - 1) / kScanTile;
-    BUILD_TRY(S.block_sums.reserve(nb));
-    LevelFlag f{S.slot_count.p, slot_lo, K + 1};
-    tile_sums_kernel<<<nb, kScanBlock, 0, stream>>>(f, n_level_slots, S.block_sums.p);
-    scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(S.block_sums.p, nb, d_total);
-    st.launches += 2;
-    BUILD_TRY(cudaStreamSynchronize(stream));
-    const uint32_t n_new = S.h_total[0];
-    if (n_new == 0) break;
-    const uint64_t want_slots = (uint64_t)n_slots + (uint64_t)n_new * K;
-    if (want_slots >= 0xFFFFFFF0ull) {
-      if (too_big) *too_big = true;
-      return cudaSuccess;
+    uint32_t level_nodes;
+    if (bounded) {
+      level_nodes = (uint32_t)ub_nodes[depth];
+    } else {
+      BUILD_TRY(read_table());
+      level_nodes = S.h_tab[4 * depth + 1];
     }
-    BUILD_TRY(grow_nodes(S, (size_t)n_nodes + n_new, n_nodes, W, stream));
-    BUILD_TRY(grow_slots(S, want_slots, n_slots, stream));
-    f.slot_count = S.slot_count.p;
-    create_children_kernel<<<nb, kScanBlock, 0, stream>>>(ptrs(S), f, n_level_slots, S.block_sums.p, level_first, n_nodes, n_slots,
-                                                          n_new, depth, W);
+    if (level_nodes == 0) break;
+    const uint32_t nb = (uint32_t)(((uint64_t)level_nodes * (K + 1) + kScanTile - 1) / kScanTile);
+    BUILD_TRY(S.block_sums.grow(nb, 0, stream));
+    LevelFlag f{S.slot_count.p, tab + 4 * depth, K + 1};
+    tile_sums_kernel<<<nb, kScanBlock, 0, stream>>>(f, tab + 4 * depth + 1, K + 1, S.block_sums.p);
+    scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(S.block_sums.p, tab + 4 * depth + 1, K + 1, tab, (int)depth, K + 1);
+    st.launches += 2;
+    if (!bounded) {
+      BUILD_TRY(read_table());
+      const uint32_t n_new = S.h_tab[4 * (depth + 1) + 1];
+      if (n_new == 0) break;
+      const uint64_t want_slots = (uint64_t)n_slots + (uint64_t)n_new * K;
+      if (want_slots >= 0xFFFFFFF0ull) {
+        if (too_big) *too_big = true;
+        return cudaSuccess;
+      }
+      BUILD_TRY(grow_nodes(S, (size_t)n_nodes + n_new, n_nodes, W, stream));
+      BUILD_TRY(grow_slots(S, want_slots, n_slots, stream));
+      n_nodes += n_new;
+      n_slots = (uint32_t)want_slots;
+      f.slot_count = S.slot_count.p;
+    }
+    create_children_kernel<<<nb, kScanBlock, 0, stream>>>(ptrs(S), f, tab, S.block_sums.p, depth, W);
     ++st.launches;
-    level_first = n_nodes;
-    level_nodes = n_new;
-    n_nodes += n_new;
-    n_slots = (uint32_t)want_slots;
-    S.level_first[depth + 1] = level_first;
   }
-  S.n_levels = depth + 1;
-  S.level_first[S.n_levels] = n_nodes;
-  st.levels = S.n_levels;
 
-  // 4. per-node totals and the observed multiset
-  BUILD_TRY(S.node_total.reserve(n_nodes));
-  node_totals_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(ptrs(S), n_nodes);
-  const uint32_t nb = (n_nodes + kScanTile - 1) / kScanTile;
-  BUILD_TRY(S.block_sums.reserve(nb));
-  ObservedFlag of{S.node_base.p, S.slot_count.p};
-  tile_sums_kernel<<<nb, kScanBlock, 0, stream>>>(of, n_nodes, S.block_sums.p);
-  scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(S.block_sums.p, nb, d_total);
-  st.launches += 3;
-  BUILD_TRY(cudaStreamSynchronize(stream));
-  const uint32_t n_obs = S.h_total[0];
-  BUILD_TRY(S.obs_key.reserve((size_t)std::max(n_obs, 1u) * W));
-  BUILD_TRY(S.obs_cnt.reserve(std::max(n_obs, 1u)));
-  BUILD_TRY(S.obs_first.reserve(std::max(n_obs, 1u)));
-  if (n_obs) {
-    ObsOut O{S.obs_key.p, S.obs_cnt.p, S.obs_tally0.p, S.obs_first.p};
-    write_observed_kernel<<<nb, kScanBlock, 0, stream>>>(ptrs(S), of, n_nodes, S.block_sums.p, O, nc, W);
-    ++st.launches;
+  // 5. per-node totals and the observed multiset
+  uint32_t nodes_launch = (uint32_t)std::min<uint64_t>(ub_total, 0xFFFFFFFFull);
+  if (!bounded) {
+    BUILD_TRY(read_table());
+    nodes_launch = S.h_tab[4 * kTotRow];
+    BUILD_TRY(S.node_total.grow(nodes_launch, 0, stream));
   }
+  node_totals_kernel<<<(nodes_launch + 255) / 256, 256, 0, stream>>>(ptrs(S), tab);
+  const uint32_t nb = (nodes_launch + kScanTile - 1) / kScanTile;
+  BUILD_TRY(S.block_sums.grow(nb, 0, stream));
+  ObservedFlag of{S.node_base.p, S.slot_count.p};
+  tile_sums_kernel<<<nb, kScanBlock, 0, stream>>>(of, tab + 4 * kTotRow, 1u, S.block_sums.p);
+  scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(S.block_sums.p, tab + 4 * kTotRow, 1u, tab, -1, 0u);
+  st.launches += 3;
+  uint64_t obs_cap = std::max<uint64_t>(n_ballots, 1);  // every entry stands for at least one ballot
+  if (!bounded) {
+    BUILD_TRY(read_table());
+    obs_cap = std::max<uint32_t>(S.h_tab[4 * kTotRow + 2], 1u);
+  }
+  BUILD_TRY(S.obs_key.grow((size_t)obs_cap * W, 0, stream));
+  BUILD_TRY(S.obs_cnt.grow(obs_cap, 0, stream));
+  BUILD_TRY(S.obs_first.grow(obs_cap, 0, stream));
+  ObsOut O{S.obs_key.p, S.obs_cnt.p, S.obs_tally0.p, S.obs_first.p};
+  write_observed_kernel<<<nb, kScanBlock, 0, stream>>>(ptrs(S), of, tab, S.block_sums.p, O, nc, W);
+  ++st.launches;
   BUILD_TRY(cudaGetLastError());
-  BUILD_TRY(cudaStreamSynchronize(stream));
-  S.n_nodes = n_nodes;
-  S.n_slots = n_slots;
-  S.n_obs = n_obs;
+  BUILD_TRY(read_table());
+  S.n_nodes = S.h_tab[4 * kTotRow];
+  S.n_slots = S.h_tab[4 * kTotRow + 1];
+  S.n_obs = S.h_tab[4 * kTotRow + 2];
   if (stats) *stats = st;
   return cudaSuccess;
 }

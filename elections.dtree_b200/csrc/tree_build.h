@@ -28,21 +28,23 @@ struct DeviceTreeStore {
   // build-time only
   DevBuf<uint64_t> node_key;
   DevBuf<uint32_t> cursor, block_sums;
-  uint32_t *h_total = nullptr;  // pinned, 2 words
-  uint32_t level_first[kMaxCandidates + 2] = {0};
-  uint32_t n_levels = 0;
+  DevBuf<uint32_t> level_tab;   // per depth {first node, nodes, first slot, -}, then {nodes, slots, observed entries, -}
+  uint32_t *h_tab = nullptr;    // pinned copy of level_tab
   void release_all();
 };
 
 struct BuildStats {
   uint64_t h2d_bytes = 0;
-  uint32_t launches = 0, levels = 0;
+  uint32_t launches = 0, host_syncs = 0;
 };
 
 // Appends ballots [S.log_ballots, n_ballots) of the host log (prefs/offsets as given to dtree_update,
 // already validated) to the device log and rebuilds the mirror. Returns a CUDA error; `too_big` is set
-// when the tree needs more than 2^32-16 slots.
+// when the tree needs more than 2^32-16 slots. When the arrays sized by a priori bounds (a level has at most
+// min(#ballots, parents x children) nodes) fit `bound_budget_bytes`, the whole build is enqueued without a host
+// round trip and synchronised once; otherwise the host reads every level's size to allocate exactly.
 cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t *h_prefs, const uint64_t *h_offsets,
-                                 uint64_t n_ballots, cudaStream_t stream, BuildStats *stats, bool *too_big);
+                                 uint64_t n_ballots, cudaStream_t stream, BuildStats *stats, bool *too_big,
+                                 uint64_t bound_budget_bytes = 1ull << 30);
 
 }  // namespace dtb
