@@ -23,7 +23,8 @@ namespace dtb {
 
 // Per-thread bookkeeping of one election (registers).
 struct LaneState {
-  uint32_t n_pool;            // high-water mark of the parked pool
+  uint32_t n_pool;            // pool slots handed out so far (fresh ones first)
+  uint32_t hw_live;           // most nodes parked at once (n_pool - n_free): what the arena has to hold (usage report)
   uint32_t n_free;            // free-list depth
   uint32_t q_head, q_tail;    // circular small-count queue (monotone counters)
   uint32_t n_big;             // waiting heavy nodes in the heap (beyond the kLaneTop kept apart)
@@ -157,6 +158,7 @@ __device__ __forceinline__ void lane_route(const SimArgs &a, LaneShared<BLOCK> &
   sc.pool[j] = ch;
   sc.holder[j] = (uint8_t)cand;
   ++st.rec_w;
+  st.hw_live = max(st.hw_live, st.n_pool - st.n_free);
 }
 
 // Split of a node with a small sampled count (0..urn_max): split_small_node of deferred.cuh without the atomics.
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
     const bool active = e < a.n_elections;
     const RngKey key = election_key(a.seed, a.first_election + e);
     LaneState st;
-    st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.n_top = 0; st.eliminated = 0; st.rec_w = 0; st.rec_r = 0;
+    st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.n_top = 0; st.eliminated = 0; st.rec_w = 0; st.rec_r = 0; st.hw_live = 0;
 #pragma unroll
     for (uint32_t k = 0; k < kLaneTop; ++k) sh.top_mass[k][tid] = 0;
     st.hw_queue = 0; st.hw_big = 0; st.unresolved = 0; st.overflow = false;
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
     if (active) {
       stat[kStatEntries] += st.rec_w;
       stat[kStatRereads] += st.rec_r;
-      usage[0] = max(usage[0], st.n_pool);
+      usage[0] = max(usage[0], st.hw_live);
       usage[1] = max(usage[1], st.hw_queue);
       usage[2] = max(usage[2], st.hw_big);
       if (st.overflow) {

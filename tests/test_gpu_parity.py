@@ -575,12 +575,18 @@ def test_full_size_configs_conserve_ballots_and_agree_across_kernels(pkg, L, nam
     assert len(set(sampled)) == len(sampled) and all(len(set(b)) == len(b) for b in sampled[:20000])
     n_el = {"C2": 3000, "C3": 400, "C4": 60}[name]
     res = {}
+    splits = {}
     for mode in (0, 1, 2):
         t.tune(mode=mode)
         res[mode] = t.sample_posterior_counts(n_el, cfg["n_ballots"], seed="FULL", return_orders=True)
         assert int(res[mode][0].sum()) == n_el
         plain = t.sample_posterior_counts(n_el, cfg["n_ballots"], seed="FULL")  # with the early-stop short-cuts
         assert plain.tolist() == res[mode][0].tolist()
+        splits[mode] = t.last_stats()["items"] / n_el
+    # the deferred kernels decide rounds without splitting what cannot matter: far fewer node splits, same outcomes
+    assert splits[1] < 0.5 * splits[0] and splits[2] < 0.5 * splits[0], splits
+    if name == "C3":
+        assert splits[2] < 50, splits
     for mode in (1, 2):
         assert res[0][0].tolist() == res[mode][0].tolist() and np.array_equal(res[0][1], res[mode][1]), mode
     # the order reported for election 5 is one the reference rule allows on election 5's ballots
