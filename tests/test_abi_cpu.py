@@ -91,6 +91,32 @@ def test_update_counts_bit_exact_vs_oracle(pkg, port, nc, mn, mx):
     assert t.n_observed == 0
 
 
+def test_update_log_accepts_offsets_that_do_not_start_at_zero_and_rejects_atomically(pkg, port):
+    """dtree_update appends to the ballot log: a CSR window into a larger array (offsets[0] != 0) is rebased, several
+    updates accumulate, a rejected batch leaves no trace, reset empties the log (R_tree.cpp:125-153, :155-...)."""
+    nc = 6
+    prefs, offsets = pkg.workloads.plackett_luce_ballots(nc, 0.3, 400, 9, np.ones(nc + 1))
+    t, o = _trees(pkg, port, nc, 0, nc)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t.update_indices(prefs, offsets[:101])    # ballots 0..99
+        t.update_indices(prefs, offsets[100:251])  # ballots 100..249 as a window: offsets[0] > 0
+        bad = prefs.copy()
+        bad[int(offsets[300])] = nc  # unknown candidate in ballot 300
+        with pytest.raises(pkg._native.DtreeError, match="Unknown candidate"):
+            t.update_indices(bad, offsets[250:])
+        assert t.n_observed == 250
+        t.update_indices(prefs, offsets[250:])
+    o.update((prefs, offsets))
+    assert t.n_observed == o.n_observed() == 400
+    assert oracle.parse_node_dump(t.export_nodes()) == oracle.parse_node_dump(o.dump_nodes())
+    t.reset()
+    o.reset()
+    assert t.n_observed == 0
+    assert oracle.parse_node_dump(t.export_nodes()) == oracle.parse_node_dump(o.dump_nodes())
+    o.close()
+
+
 def test_update_matches_recorded_reference_dumps(pkg, ref_vectors):
     """tests/golden/ref_vectors.json was written by the unmodified reference."""
     for case in ref_vectors:
