@@ -80,6 +80,33 @@ enum OutStat {
   kOutH2D, kOutD2H, kOutSlots, kOutUrnItems, kOutMode, kOutArenaRuns, kOutBuildLaunches, kOutCount = 16
 };
 
+// A host range page-locked for direct DMA (the ballot log: it travels to the device whenever the mirror is rebuilt
+// from host memory). Failure to lock is not an error: the copy is then staged by the driver as for any pageable memory.
+struct PinnedRange {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+static void unpin(PinnedRange &r) {
+  if (r.p) {
+    cudaHostUnregister(r.p);
+    cudaGetLastError();
+  }
+  r = PinnedRange();
+}
+
+static void pin(PinnedRange &r, const void *p, size_t bytes) {
+  if (r.p == p && r.bytes == bytes) return;
+  unpin(r);
+  if (!p || bytes < (1u << 16)) return;  // small logs: not worth the page-locking
+  if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+    r.p = const_cast<void *>(p);
+    r.bytes = bytes;
+  } else {
+    cudaGetLastError();
+  }
+}
+
 struct dtree_ballots {
   std::vector<uint8_t> prefs;
   std::vector<uint64_t> offsets{0};
@@ -91,6 +118,7 @@ struct dtree {
   // (tree_build.cu); the host trie below is brought up to date only for the host-side exports.
   std::vector<uint8_t> log_prefs;
   std::vector<uint64_t> log_offsets{0};
+  PinnedRange pin_prefs, pin_offsets;  // the two vectors' buffers while page-locked (dropped before they can move)
   uint64_t n_observed = 0, depth_mask = 0, version = 0;  // version: bumped by update/reset
   HostTree tree;              // parameters (tree.P) + lazily synchronised trie
   uint64_t trie_ballots = 0;  // log entries already inserted into `tree`
@@ -160,6 +188,13 @@ DeviceParams device_params(const HostParams &P) {
   return D;
 }
 
+void unpin_log(dtree *t) {
+  if (!t->pin_prefs.p && !t->pin_offsets.p) return;
+  DeviceGuard g(t->device);
+  unpin(t->pin_prefs);
+  unpin(t->pin_offsets);
+}
+
 // Brings the host trie up to date with the ballot log.
 void sync_trie(dtree *t) {
   const uint64_t n = t->log_offsets.size() - 1;
@@ -198,6 +233,8 @@ int ensure_host_image(dtree *t) {
 int ensure_mirror(dtree *t, cudaStream_t s) {
   if (t->mirrored_version == t->version) return DTREE_OK;
   if (!t->host_build) {
+    pin(t->pin_prefs, t->log_prefs.data(), t->log_prefs.capacity());
+    pin(t->pin_offsets, t->log_offsets.data(), t->log_offsets.capacity() * sizeof(uint64_t));
     BuildStats bs;
     bool too_big = false;
     CUDA_TRY(build_tree_on_device(t->dev, t->tree.P.nc, t->log_prefs.data(), t->log_offsets.data(),
@@ -772,6 +809,7 @@ int dtree_destroy(dtree_t *t) {
   if (!t) return DTREE_OK;
   for (dtree *r : t->replicas) dtree_destroy(r);
   t->replicas.clear();
+  unpin_log(t);
   if (t->sm_count) {
     DeviceGuard g(t->device);
     t->dev.release_all();
@@ -826,10 +864,10 @@ int dtree_update(dtree_t *t, const uint8_t *prefs, const uint64_t *offsets, uint
   std::string err;
   uint64_t mask = 0;
   if (!t->tree.P.validate(prefs, offsets, n, n_short, &mask, err)) return fail(DTREE_ERR_ARG, "%s", err.c_str());
-  // append to the log, offsets rebased onto it
+  // append to the log, offsets rebased onto it (a buffer that has to grow stops being page-locked first)
   const uint64_t at = t->log_prefs.size(), first = offsets[0];
+  if (at + (offsets[n] - first) > t->log_prefs.capacity() || t->log_offsets.size() + n > t->log_offsets.capacity()) unpin_log(t);
   t->log_prefs.insert(t->log_prefs.end(), prefs + first, prefs + offsets[n]);
-  t->log_offsets.reserve(t->log_offsets.size() + n);
   for (uint64_t i = 1; i <= n; ++i) t->log_offsets.push_back(at + (offsets[i] - first));
   t->n_observed += n;  // R_tree.cpp:149
   t->depth_mask |= mask;
@@ -988,6 +1026,7 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
     }
     if (!r) r = new dtree(t->tree.P, dev);
     if (r->version != t->version || r->n_observed != t->n_observed) {  // same ballot log, own mirror
+      unpin_log(r);
       r->log_prefs = t->log_prefs;
       r->log_offsets = t->log_offsets;
       r->n_observed = t->n_observed;
