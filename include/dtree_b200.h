@@ -180,8 +180,10 @@ int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user
  * key: "mode" — how dtree_sample_posterior* simulates an election: 1 and 2 expand a tree node only when IRV
  *        needs to look below it, with a warp (1) or a single thread (2) per election; 0 materialises every
  *        sampled ballot first, as the reference does (dirichlet_tree.h:216-235 then irv_ballot.cpp:42-138);
- *        -1 (default) picks 2 when there are enough elections to fill the GPU with one per thread, else 1,
- *        and 0 only if the worst-case scratch of 1/2 does not fit the device. All give bit-identical outcomes;
+ *        -1 (default) picks 2 when there are enough elections to fill the GPU with one per thread and an election
+ *        needs at most a few thousand node splits (measured on the first elections of the call), else 1, and 0 only
+ *        if the worst-case scratch of 1/2 does not fit the device. All give bit-identical outcomes; forcing 2 on
+ *        elections that need tens of thousands of splits (very close races, 20 candidates) is correct but slow;
  *      "block_threads" (0 = auto), "blocks_per_sm" (0 = auto), "urn_max" (largest count split by the
  *        Polya-urn shortcut instead of Gamma variates, <= 8);
  *      "host_build" (0 default; 1 = build the tree with the host trie and upload it, the pre-device-build
