@@ -161,10 +161,11 @@ class dirichlet_tree:
         return self
 
     def last_stats(self):
-        buf = (C.c_uint64 * 16)()
-        N.check(self._L.dtree_last_stats(self._h, buf, 16))
+        buf = (C.c_uint64 * 24)()
+        N.check(self._L.dtree_last_stats(self._h, buf, 24))
         keys = ["launches", "elections", "entries", "items", "gammas", "binomial_attempts", "irv_rereads",
-                "scratch_bytes", "h2d_bytes", "d2h_bytes", "slots", "urn_items", "mode", "arena_runs", "build_launches"]
+                "scratch_bytes", "h2d_bytes", "d2h_bytes", "slots", "urn_items", "mode", "arena_runs", "build_launches",
+                "lane_retries", "mirror_us", "plan_us", "launch_us", "finish_us"]
         return {k: int(buf[i]) for i, k in enumerate(keys)}
 
     _IMAGE_ARRAYS = {"node_base": (0, "uint32"), "node_total": (1, "uint32"), "slot_count": (2, "uint32"),
@@ -253,6 +254,8 @@ class dirichlet_tree:
                                 first_election=0, return_orders=False, devices=None):
         if n_elections <= 0:
             raise ValueError("`n_elections` must be an integer > 0.")
+        if n_elections > 0xFFFFFFFF or n_ballots > 0xFFFFFFFF:  # unsigned in the reference too (R_tree.h:86-88)
+            raise ValueError("`n_elections` and `n_ballots` must be < 2^32.")
         if n_ballots < self.n_observed and not replace:
             raise ValueError("`n_ballots` must be an integer >= the number of observed ballots unless sampling "
                              "with replacement.")

@@ -3,7 +3,10 @@
 // arithmetic runs on the host: if CUDA is unusable every sampling entry point fails.
 #include <cuda_runtime.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -77,8 +80,33 @@ double falling_factorial(uint32_t n, uint32_t k) {
 // Layout of dtree_last_stats (include/dtree_b200.h).
 enum OutStat {
   kOutLaunches = 0, kOutElections, kOutEntries, kOutItems, kOutGammas, kOutBinomials, kOutRereads, kOutScratchBytes,
-  kOutH2D, kOutD2H, kOutSlots, kOutUrnItems, kOutMode, kOutArenaRuns, kOutBuildLaunches, kOutCount = 16
+  kOutH2D, kOutD2H, kOutSlots, kOutUrnItems, kOutMode, kOutArenaRuns, kOutBuildLaunches, kOutLaneRetries,
+  kOutMirrorUs, kOutPlanUs, kOutLaunchUs, kOutFinishUs, kOutCount = 24
 };
+
+// NVTX range over a scope (the reference has no tracing; these show up in Nsight Systems / ncu --nvtx).
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+struct HostTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  uint64_t us() const {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+
+// Everything a sampling call reads back, contiguous on the device so that one copy into page-locked memory fetches it.
+struct ResultBlock {
+  unsigned long long wins[kMaxCandidates];
+  unsigned long long stats[8];  // kStatCount <= 8
+  unsigned int usage[8];        // [0..2] arena high-water marks, [3] elections re-run in a worst-case arena, [4] lane retries
+  int error;
+  unsigned int counter;         // work counter of the running launch
+  unsigned int pad_[2];
+};
+static_assert(kStatCount <= 8, "ResultBlock::stats too small");
 
 // A host range page-locked for direct DMA (the ballot log: it travels to the device whenever the mirror is rebuilt
 // from host memory). Failure to lock is not an error: the copy is then staged by the driver as for any pageable memory.
@@ -136,14 +164,13 @@ struct dtree {
   DeviceTreeStore dev;  // tree arrays, packed observed ballots, ballot log (tree_build.h)
   // scratch + small device state
   DevBuf<uint8_t> d_scratch;
-  DevBuf<unsigned long long> d_wins, d_stats;
-  DevBuf<unsigned int> d_counter;
-  DevBuf<int> d_error;
+  DevBuf<ResultBlock> d_res;
+  ResultBlock *h_res = nullptr;  // page-locked
   DevBuf<uint32_t> d_entry_count;
   DevBuf<uint8_t> d_orders;
-  // deferred kernel: worst-case overflow arenas, their locks, usage high-water marks [3] + arena runs [1]
+  // deferred kernel: worst-case overflow arenas and their locks; lane kernel: the retry list ([0] count, [4..] elections)
   DevBuf<uint8_t> d_arena;
-  DevBuf<unsigned int> d_locks, d_usage, d_retry;  // d_retry: [0] count, [4..] election indices
+  DevBuf<unsigned int> d_locks, d_retry;
   struct Sizing {
     bool valid = false;
     uint64_t version = 0;
@@ -158,6 +185,8 @@ struct dtree {
   // tuning
   int block_threads = 0, blocks_per_sm = 0;
   uint32_t urn_max = 8;
+  uint32_t arena_cap = 0;        // > 0: per-warp / per-thread arenas hold at most this many items (forces the overflow paths)
+  int64_t lane_max_splits = -1;  // lane_kernel hands an election to the replay after this many splits (-1 auto, 0 never)
   int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
   // replicas on other devices for dtree_sample_posterior_multi (owned; same parameters, tree copied when stale)
   std::vector<dtree *> replicas;
@@ -402,9 +431,9 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
   a.cap_entries = pl.cap_entries;
   a.cap_queue = pl.cap_queue;
   a.cap_big = pl.cap_big;
-  a.work_counter = t->d_counter.p;
-  a.error_flag = t->d_error.p;
-  a.stats = t->d_stats.p;
+  a.work_counter = &t->d_res.p->counter;
+  a.error_flag = &t->d_res.p->error;
+  a.stats = t->d_res.p->stats;
 }
 
 cudaError_t launch(const Plan &pl, const SimArgs &a, cudaStream_t s) {
@@ -419,6 +448,16 @@ int check_sampling_args(dtree *t, uint32_t n_ballots, const char *seed, size_t s
   if (!seed && seed_len) return fail(DTREE_ERR_ARG, "null seed");
   if (t->tree.P.vd && t->tree.P.max_depth == 0)
     return fail(DTREE_ERR_ARG, "vd requires max_depth >= 1 (the reference reads depthFactors out of bounds here)");
+  // The kernels carry the prior parameters a0 * depthFactor[d] and sums of up to 33 Gamma variates of about that size
+  // in float: beyond this bound they would overflow to inf (vd at 32 candidates reaches 32! = 2.6e35 times a0).
+  {
+    const HostParams &P = t->tree.P;
+    double worst = P.a0;
+    if (P.vd)
+      for (double f : P.depth_factors) worst = std::max(worst, P.a0 * f);
+    if (!(worst <= 1e36))
+      return fail(DTREE_ERR_ARG, "a0 times the largest depth factor is %.3g; the device sampler supports at most 1e36", worst);
+  }
   (void)n_ballots;
   return DTREE_OK;
 }
@@ -433,42 +472,89 @@ void store_kernel_counters(dtree *t, const unsigned long long *st) {
   t->stats[kOutUrnItems] = st[kStatUrnItems];
 }
 
-// Reads the deferred kernel's high-water marks and grows the cached sizing if an election came close.
-int absorb_usage(dtree *t) {
-  if (!t->d_usage.p) return DTREE_OK;
-  unsigned int u[4];
-  CUDA_TRY(cudaMemcpy(u, t->d_usage.p, sizeof u, cudaMemcpyDeviceToHost));
-  dtree::Sizing &z = t->sizing;
-  if (z.valid) {
-    z.pool = std::max(z.pool, u[0]);
-    z.queue = std::max(z.queue, u[1]);
-    z.big = std::max(z.big, u[2]);
-  }
-  t->stats[kOutArenaRuns] = u[3];
-  if (z.valid && t->stats[kOutElections] > 0 && t->stats[kOutItems] > 0)
-    z.nodes_per_election = (double)t->stats[kOutItems] / (double)t->stats[kOutElections];
+// The device result block and its page-locked host copy.
+int ensure_result_block(dtree *t) {
+  CUDA_TRY(t->d_res.reserve(1));
+  if (!t->h_res) CUDA_TRY(cudaHostAlloc((void **)&t->h_res, sizeof(ResultBlock), cudaHostAllocDefault));
   return DTREE_OK;
 }
 
-// Common body of the two sample_posterior entry points. d_wins must be device memory on t->device.
-int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots, uint32_t n_winners,
-                  int replace, const char *seed, size_t seed_len, unsigned long long *d_wins, uint8_t *h_orders,
-                  cudaStream_t s, bool sync_at_end) {
+// The counters a call reports are its own (dtree_last_stats: "of the last sampling call").
+void begin_call_stats(dtree *t) {
+  for (int i = 0; i < kOutCount; ++i)
+    if (i != kOutBuildLaunches && i != kOutScratchBytes) t->stats[i] = 0;
+}
+
+// Waits for the stream, fetches the result block with one copy and digests it: kernel-side failure, counters,
+// arena usage (which grows the cached sizing if an election came close to its capacity).
+int fetch_results(dtree *t, cudaStream_t s) {
+  NvtxRange nv("dtree:read_back");
+  HostTimer tm;
+  CUDA_TRY(cudaMemcpyAsync(t->h_res, t->d_res.p, sizeof(ResultBlock), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  t->stats[kOutD2H] += sizeof(ResultBlock);
+  t->stats[kOutFinishUs] += tm.us();
+  const ResultBlock &R = *t->h_res;
+  if (R.error) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed (code %d)", R.error);
+  store_kernel_counters(t, R.stats);
+  if (t->stats[kOutMode] >= 1) {
+    dtree::Sizing &z = t->sizing;
+    if (z.valid) {
+      z.pool = std::max(z.pool, R.usage[0]);
+      z.queue = std::max(z.queue, R.usage[1]);
+      z.big = std::max(z.big, R.usage[2]);
+      if (t->stats[kOutElections] > 0 && t->stats[kOutItems] > 0)
+        z.nodes_per_election = (double)t->stats[kOutItems] / (double)t->stats[kOutElections];
+    }
+    t->stats[kOutArenaRuns] = R.usage[3];
+    t->stats[kOutLaneRetries] = R.usage[4];
+  }
+  return DTREE_OK;
+}
+
+// One sample_posterior job on one device: prepared once, launched wave by wave (so that several devices can be
+// driven from one host thread and the abort callback can be polled between waves), then read back.
+struct Job {
+  dtree *t = nullptr;
+  cudaStream_t s = 0;
+  Plan pl, pp;    // the main launch; the pilot / replay launch of deferred_kernel
+  SimArgs a, ar;  // their arguments (ar: replay of the elections lane_kernel could not finish)
+  uint32_t nc = 0;
+  uint64_t first_election = 0, n_elections = 0, done = 0, pilot_done = 0, wave = 0, launches = 0;
+  bool want_orders = false;
+};
+
+int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots, uint32_t n_winners,
+                int replace, const char *seed, size_t seed_len, unsigned long long *d_wins, bool want_orders,
+                cudaStream_t s) {
+  j.t = t;
+  j.s = s;
+  j.first_election = first_election;
+  j.n_elections = n_elections;
+  j.want_orders = want_orders;
   int rc = check_sampling_args(t, n_ballots, seed, seed_len);
   if (rc) return rc;
-  const uint32_t nc = t->tree.P.nc;
+  const uint32_t nc = j.nc = t->tree.P.nc;
   if ((uint64_t)n_ballots < t->n_observed)  // R_tree.cpp:183-186
     return fail(DTREE_ERR_STATE, "`nBallots` must be larger than the number of ballots observed to obtain the posterior.");
   if (n_winners < 1 || n_winners >= nc) return fail(DTREE_ERR_ARG, "n_winners must be in [1, n_candidates)");
   if (n_elections == 0) return DTREE_OK;
-  rc = ensure_mirror(t, s);
-  if (rc) return rc;
+  {
+    NvtxRange nv("dtree:mirror");
+    HostTimer tm;
+    rc = ensure_mirror(t, s);
+    t->stats[kOutMirrorUs] += tm.us();
+    if (rc) return rc;
+  }
+  NvtxRange nv_plan("dtree:plan");
+  HostTimer tm_plan;
   const bool use_obs = !replace;
   const uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->n_observed;
-  Plan pl;
+  Plan &pl = j.pl, &pp = j.pp;
+  pl = Plan();
   pl.deferred = t->mode == 1 || t->mode == 2;
   bool want_lane = t->mode == 2;
-  if (t->mode < 0) pl.deferred = true;  // the deferred kernel is the faster one on every configuration measured
+  if (t->mode < 0) pl.deferred = true;  // the deferred kernels are the faster ones on every configuration measured
   if (pl.deferred) {
     rc = make_plan_deferred(t, n_sample, n_elections, pl);
     if (rc) return rc;
@@ -478,15 +564,13 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     rc = make_plan(t, n_sample, n_elections, use_obs, pl);
     if (rc) return rc;
   }
-  CUDA_TRY(t->d_counter.reserve(1));
-  CUDA_TRY(t->d_error.reserve(1));
-  CUDA_TRY(t->d_stats.reserve(kStatCount));
-  CUDA_TRY(cudaMemsetAsync(t->d_error.p, 0, sizeof(int), s));
-  CUDA_TRY(cudaMemsetAsync(t->d_stats.p, 0, kStatCount * sizeof(unsigned long long), s));
-  if (h_orders) CUDA_TRY(t->d_orders.reserve((size_t)n_elections * nc));
+  rc = ensure_result_block(t);
+  if (rc) return rc;
+  ResultBlock *R = t->d_res.p;
+  // error flag, counters and usage start at zero; the win counts are the caller's business (they are added to)
+  CUDA_TRY(cudaMemsetAsync(&R->stats[0], 0, sizeof(ResultBlock) - offsetof(ResultBlock, stats), s));
+  if (want_orders) CUDA_TRY(t->d_orders.reserve((size_t)n_elections * nc));
 
-  SimArgs a;
-  memset(&a, 0, sizeof a);
   auto fill_job = [&](const Plan &plan, SimArgs &a) {
     fill_args(t, plan, a);
     a.obs_key = t->dev.obs_key.p;
@@ -503,23 +587,21 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
   };
 
   uint32_t pilot_done = 0;
-  uint64_t launches = 0;
-  Plan pp;  // pilot / replay launches of deferred_kernel in the worst-case arenas
+  bool replay = false;
   if (pl.deferred) {
     const HostParams &P = t->tree.P;
     dtree::Sizing &z = t->sizing;
     const bool hit = z.valid && z.version == t->version && z.n_sample == n_sample && z.urn_max == t->urn_max &&
                      z.min_depth == P.min_depth && z.max_depth == P.max_depth && z.a0 == P.a0 && z.vd == P.vd &&
-                     z.use_obs == use_obs && z.short_cuts == (n_winners == 1 && h_orders == nullptr);
+                     z.use_obs == use_obs && z.short_cuts == (n_winners == 1 && !want_orders);
     CUDA_TRY(t->d_arena.reserve(pl.arena_stride * pl.n_arenas));
     // Arena locks start free at every call: a launch that died must not leave one held.
     CUDA_TRY(t->d_locks.reserve(kMaxArenas));
     CUDA_TRY(cudaMemsetAsync(t->d_locks.p, 0, kMaxArenas * sizeof(unsigned int), s));
-    CUDA_TRY(t->d_usage.reserve(4));
-    CUDA_TRY(cudaMemsetAsync(t->d_usage.p, 0, 4 * sizeof(unsigned int), s));
     if (!hit) {
       // Pilot: a few elections run directly in the worst-case arenas (they cannot overflow and their
       // results count); their high-water marks size everybody else's arena.
+      NvtxRange nv("dtree:pilot");
       pp = pl;
       pp.cap_items = pl.arena_items;
       pp.cap_queue = pl.arena_queue;
@@ -534,25 +616,24 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
       ap.scratch_stride = pl.arena_stride;
       ap.max_warps = pl.n_arenas;
       ap.n_arenas = 0;
-      ap.usage = t->d_usage.p;
-      ap.arena_runs = t->d_usage.p + 3;
+      ap.usage = R->usage;
+      ap.arena_runs = R->usage + 3;
       ap.first_election = first_election;
       ap.n_elections = pilot_done;
-      ap.elim_orders = h_orders ? t->d_orders.p : nullptr;
-      CUDA_TRY(cudaMemsetAsync(t->d_counter.p, 0, sizeof(unsigned int), s));
+      ap.elim_orders = want_orders ? t->d_orders.p : nullptr;
+      CUDA_TRY(cudaMemsetAsync(&R->counter, 0, sizeof(unsigned int), s));
       CUDA_TRY(launch(pp, ap, s));
-      ++launches;
+      ++j.launches;
+      CUDA_TRY(cudaMemcpyAsync(t->h_res, R, sizeof(ResultBlock), cudaMemcpyDeviceToHost, s));
       CUDA_TRY(cudaStreamSynchronize(s));
-      unsigned int u[4];
-      CUDA_TRY(cudaMemcpy(u, t->d_usage.p, sizeof u, cudaMemcpyDeviceToHost));
+      t->stats[kOutD2H] += sizeof(ResultBlock);
+      const ResultBlock &H = *t->h_res;
       z.valid = true;
       z.version = t->version;
       z.n_sample = n_sample; z.urn_max = t->urn_max; z.min_depth = P.min_depth; z.max_depth = P.max_depth;
-      z.a0 = P.a0; z.vd = P.vd; z.use_obs = use_obs; z.short_cuts = n_winners == 1 && h_orders == nullptr;
-      z.pool = u[0]; z.queue = u[1]; z.big = u[2];
-      unsigned long long st[kStatCount];
-      CUDA_TRY(cudaMemcpy(st, t->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
-      z.nodes_per_election = (double)st[kStatItems] / std::max<uint32_t>(pilot_done, 1);
+      z.a0 = P.a0; z.vd = P.vd; z.use_obs = use_obs; z.short_cuts = n_winners == 1 && !want_orders;
+      z.pool = H.usage[0]; z.queue = H.usage[1]; z.big = H.usage[2];
+      z.nodes_per_election = (double)H.stats[kStatItems] / std::max<uint32_t>(pilot_done, 1);
     }
     // Capacities get a 4x margin over the largest election seen and are only revised when an election has
     // used more than half of them (so that a new maximum does not reallocate the scratch every time).
@@ -564,7 +645,7 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     pl.cap_big = std::min(z.cap_big, pl.arena_big);
     // One thread per election (lane_kernel): 32x more arenas in flight, so a tighter margin (3x the largest election
     // seen, revised only when an election has used more than 75 % of it); an election that still outgrows its arena
-    // is replayed by deferred_kernel in a worst-case arena.
+    // is replayed by deferred_kernel.
     if (!hit || 4ull * z.pool > 3ull * z.lane_pool) z.lane_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 3ull * z.pool + 512);
     if (!hit || 4ull * z.queue > 3ull * z.lane_queue) z.lane_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 3ull * z.queue + 512);
     // (the lane kernel's heap also holds small-count nodes that carry many observed ballots, which the pilot's warp
@@ -577,6 +658,14 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
     lp.cap_items = std::min(z.lane_pool, pl.arena_items);
     lp.cap_queue = std::min(z.lane_queue, pl.arena_queue);
     lp.cap_big = std::min(z.lane_big, pl.arena_items);
+    if (t->arena_cap) {  // test hook: arenas far too small, so that the overflow / replay paths run
+      pl.cap_items = std::min(pl.cap_items, t->arena_cap);
+      pl.cap_queue = std::min(pl.cap_queue, t->arena_cap);
+      pl.cap_big = std::min(pl.cap_big, t->arena_cap);
+      lp.cap_items = std::min(lp.cap_items, t->arena_cap);
+      lp.cap_queue = std::min(lp.cap_queue, t->arena_cap);
+      lp.cap_big = std::min(lp.cap_big, t->arena_cap);
+    }
     lp.stride = (deferred_scratch_bytes(lp.cap_items, lp.cap_queue, lp.cap_big) + 255) & ~255ull;  // per thread
     lp.stride_block = lp.stride * lp.block;
     {
@@ -598,102 +687,123 @@ int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint3
                     z.nodes_per_election <= 5000.0;
       }
     }
+    shape_deferred(t, std::min<uint32_t>(n_elections - pilot_done, 1u << 20), pl);
     if (want_lane) {
-      pp = pl;  // the replay launch: deferred_kernel, one warp per worst-case arena
-      pp.cap_items = pl.arena_items;
-      pp.cap_queue = pl.arena_queue;
-      pp.cap_big = pl.arena_big;
-      pp.stride = pl.arena_stride;
-      pp.block = 128;
-      pp.grid = (int)((pl.n_arenas + 3) / 4);
+      // The replay launch: the elections lane_kernel gave up on, by deferred_kernel — a warp each in the arenas a
+      // warp-per-election launch would use (the two launches follow each other on the stream, so those alias
+      // lane_kernel's scratch), with the worst-case arenas behind them.
+      pp = pl;
       pl = lp;
+      replay = true;
       CUDA_TRY(t->d_retry.reserve((1u << 20) + 4));
-    } else {
-      shape_deferred(t, n_elections - pilot_done, pl);
     }
   }
-  CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));
+  uint64_t scratch = pl.stride_block * pl.grid;
+  if (replay) scratch = std::max<uint64_t>(scratch, pp.stride_block * pp.grid);
+  CUDA_TRY(t->d_scratch.reserve(scratch));
+  SimArgs &a = j.a, &ar = j.ar;
   fill_job(pl, a);
-  if (pl.deferred) {
-    a.arena_scratch = t->d_arena.p;
-    a.arena_stride = pl.arena_stride;
-    a.n_arenas = pl.n_arenas;
-    a.arena_cap_items = pl.arena_items;
-    a.arena_cap_queue = pl.arena_queue;
-    a.arena_cap_big = pl.arena_big;
-    a.arena_locks = t->d_locks.p;
-    a.usage = t->d_usage.p;
-    a.arena_runs = t->d_usage.p + 3;
-    a.max_warps = 0xFFFFFFFFu;
-  }
-
-  SimArgs ar;  // lane mode: the replay of overflowed elections, enqueued right behind every wave
-  if (pl.lane) {
+  auto deferred_fields = [&](SimArgs &x) {
+    x.arena_scratch = t->d_arena.p;
+    x.arena_stride = pl.arena_stride;
+    x.n_arenas = pl.n_arenas;
+    x.arena_cap_items = pl.arena_items;
+    x.arena_cap_queue = pl.arena_queue;
+    x.arena_cap_big = pl.arena_big;
+    x.arena_locks = t->d_locks.p;
+    x.usage = R->usage;
+    x.arena_runs = R->usage + 3;
+    x.max_warps = 0xFFFFFFFFu;
+  };
+  if (pl.deferred) deferred_fields(a);
+  if (replay) {
     a.retry_list = t->d_retry.p + 4;
     a.retry_count = t->d_retry.p;
     a.retry_cap = 1u << 20;
     a.n_arenas = 0;
+    a.lane_max_splits = t->lane_max_splits > 0 ? (uint32_t)std::min<int64_t>(t->lane_max_splits, 0xFFFFFFFFll) : 0u;
     fill_job(pp, ar);
-    ar.scratch = t->d_arena.p;
-    ar.scratch_stride = pl.arena_stride;
-    ar.max_warps = pl.n_arenas;
-    ar.n_arenas = 0;
-    ar.usage = t->d_usage.p;
-    ar.arena_runs = t->d_usage.p + 3;
+    deferred_fields(ar);
     ar.election_list = t->d_retry.p + 4;
     ar.n_elections_ptr = t->d_retry.p;
   }
   // One launch per wave. Without an abort callback the whole range is one wave (lane mode: at most 2^20
   // elections per wave, the capacity of its replay list).
-  uint32_t wave = n_elections;
-  if (t->should_abort) wave = (uint32_t)std::min<uint64_t>(n_elections, (uint64_t)pl.grid * (pl.lane ? 1024 : pl.deferred ? 4096 : 64));
-  if (pl.lane) wave = std::min<uint32_t>(wave, 1u << 20);
-  for (uint32_t done = pilot_done; done < n_elections; done += wave) {
-    uint32_t n = std::min(wave, n_elections - done);
-    if (t->should_abort && done > pilot_done) {
+  j.wave = n_elections;
+  if (t->should_abort) j.wave = std::min<uint64_t>(n_elections, (uint64_t)pl.grid * (pl.lane ? 1024 : pl.deferred ? 4096 : 64));
+  if (pl.lane) j.wave = std::min<uint64_t>(j.wave, 1u << 20);
+  j.wave = std::max<uint64_t>(j.wave, 1);
+  j.done = j.pilot_done = pilot_done;
+  t->stats[kOutElections] = n_elections;
+  t->stats[kOutScratchBytes] = scratch;
+  t->stats[kOutMode] = pl.lane ? 2 : pl.deferred ? 1 : 0;
+  t->stats[kOutPlanUs] += tm_plan.us();
+  return DTREE_OK;
+}
+
+// Enqueues the next wave of elections (and, in lane mode, the replay of those it could not finish).
+int job_launch_wave(Job &j) {
+  if (j.done >= j.n_elections) return DTREE_OK;
+  NvtxRange nv(j.pl.lane ? "dtree:lane_kernel" : j.pl.deferred ? "dtree:deferred_kernel" : "dtree:simulate_kernel");
+  HostTimer tm;
+  dtree *t = j.t;
+  ResultBlock *R = t->d_res.p;
+  const uint32_t n = (uint32_t)std::min<uint64_t>(j.wave, j.n_elections - j.done);
+  SimArgs &a = j.a;
+  a.work_counter = &R->counter;
+  a.error_flag = &R->error;
+  a.stats = R->stats;
+  a.first_election = j.first_election + j.done;
+  a.n_elections = n;
+  a.elim_orders = j.want_orders ? t->d_orders.p + (size_t)j.done * j.nc : nullptr;
+  CUDA_TRY(cudaMemsetAsync(&R->counter, 0, sizeof(unsigned int), j.s));
+  if (j.pl.lane) CUDA_TRY(cudaMemsetAsync(t->d_retry.p, 0, sizeof(unsigned int), j.s));
+  CUDA_TRY(launch(j.pl, a, j.s));
+  ++j.launches;
+  if (j.pl.lane) {
+    NvtxRange nv2("dtree:replay");
+    SimArgs &ar = j.ar;
+    ar.work_counter = &R->counter;
+    ar.error_flag = &R->error;
+    ar.stats = R->stats;
+    ar.first_election = a.first_election;
+    ar.n_elections = n;
+    ar.elim_orders = a.elim_orders;
+    CUDA_TRY(cudaMemsetAsync(&R->counter, 0, sizeof(unsigned int), j.s));
+    Plan replay = j.pp;
+    replay.deferred = true;
+    replay.lane = false;
+    CUDA_TRY(launch(replay, ar, j.s));
+    ++j.launches;
+  }
+  j.done += n;
+  t->stats[kOutLaunches] = j.launches;
+  t->stats[kOutLaunchUs] += tm.us();
+  return DTREE_OK;
+}
+
+// Common body of the sample_posterior entry points. d_wins must be device memory on t->device.
+int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots, uint32_t n_winners,
+                  int replace, const char *seed, size_t seed_len, unsigned long long *d_wins, uint8_t *h_orders,
+                  cudaStream_t s, bool sync_at_end) {
+  Job j;
+  int rc = job_prepare(j, t, first_election, n_elections, n_ballots, n_winners, replace, seed, seed_len, d_wins,
+                       h_orders != nullptr, s);
+  if (rc || n_elections == 0) return rc;
+  while (j.done < j.n_elections) {
+    if (t->should_abort && j.done > j.pilot_done) {
       CUDA_TRY(cudaStreamSynchronize(s));
       if (t->should_abort(t->abort_user)) return fail(DTREE_ERR_ABORTED, "aborted by the host");
     }
-    a.first_election = first_election + done;
-    a.n_elections = n;
-    a.elim_orders = h_orders ? t->d_orders.p + (size_t)done * nc : nullptr;
-    CUDA_TRY(cudaMemsetAsync(t->d_counter.p, 0, sizeof(unsigned int), s));
-    if (pl.lane) CUDA_TRY(cudaMemsetAsync(t->d_retry.p, 0, sizeof(unsigned int), s));
-    CUDA_TRY(launch(pl, a, s));
-    ++launches;
-    if (pl.lane) {
-      ar.first_election = a.first_election;
-      ar.n_elections = std::min<uint32_t>(n, 1u << 20);
-      ar.elim_orders = a.elim_orders;
-      CUDA_TRY(cudaMemsetAsync(t->d_counter.p, 0, sizeof(unsigned int), s));
-      Plan replay = pp;
-      replay.deferred = true;
-      replay.lane = false;
-      CUDA_TRY(launch(replay, ar, s));
-      ++launches;
-    }
-  }
-  t->stats[kOutLaunches] = launches;
-  t->stats[kOutElections] = n_elections;
-  t->stats[kOutScratchBytes] = pl.stride_block * pl.grid;
-  t->stats[kOutMode] = pl.lane ? 2 : pl.deferred ? 1 : 0;
-  if (!sync_at_end) return DTREE_OK;
-  CUDA_TRY(cudaStreamSynchronize(s));
-  int err = 0;
-  unsigned long long st[kStatCount];
-  CUDA_TRY(cudaMemcpy(&err, t->d_error.p, sizeof err, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(st, t->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
-  if (err) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
-  store_kernel_counters(t, st);
-  if (pl.deferred) {
-    rc = absorb_usage(t);
+    rc = job_launch_wave(j);
     if (rc) return rc;
   }
+  if (!sync_at_end) return DTREE_OK;
   if (h_orders) {
-    CUDA_TRY(cudaMemcpy(h_orders, t->d_orders.p, (size_t)n_elections * nc, cudaMemcpyDeviceToHost));
-    t->stats[kOutD2H] += (uint64_t)n_elections * nc;
+    CUDA_TRY(cudaMemcpyAsync(h_orders, t->d_orders.p, (size_t)n_elections * j.nc, cudaMemcpyDeviceToHost, s));
+    t->stats[kOutD2H] += (uint64_t)n_elections * j.nc;
   }
-  return DTREE_OK;
+  return fetch_results(t, s);
 }
 
 // Expansion of ONE election without IRV; copies the sampled entries back.
@@ -707,15 +817,11 @@ int run_dump(dtree *t, uint64_t election, uint32_t n_sample, const char *seed, s
   if (rc) return rc;
   pl.grid = 1;
   CUDA_TRY(t->d_scratch.reserve(pl.stride));
-  CUDA_TRY(t->d_counter.reserve(1));
-  CUDA_TRY(t->d_error.reserve(1));
-  CUDA_TRY(t->d_stats.reserve(kStatCount));
+  rc = ensure_result_block(t);
+  if (rc) return rc;
   CUDA_TRY(t->d_entry_count.reserve(1));
-  CUDA_TRY(t->d_wins.reserve(kMaxCandidates));
-  CUDA_TRY(cudaMemsetAsync(t->d_error.p, 0, sizeof(int), s));
-  CUDA_TRY(cudaMemsetAsync(t->d_counter.p, 0, sizeof(unsigned int), s));
+  CUDA_TRY(cudaMemsetAsync(t->d_res.p, 0, sizeof(ResultBlock), s));
   CUDA_TRY(cudaMemsetAsync(t->d_entry_count.p, 0, sizeof(uint32_t), s));
-  CUDA_TRY(cudaMemsetAsync(t->d_stats.p, 0, kStatCount * sizeof(unsigned long long), s));
   SimArgs a;
   fill_args(t, pl, a);
   a.seed = hash_seed(seed, seed_len);
@@ -724,14 +830,13 @@ int run_dump(dtree *t, uint64_t election, uint32_t n_sample, const char *seed, s
   a.n_sample = n_sample;
   a.n_winners = 1;
   a.run_irv = 0;
-  a.win_counts = t->d_wins.p;
+  a.win_counts = t->d_res.p->wins;
   a.entry_count_out = t->d_entry_count.p;
   CUDA_TRY(launch(pl, a, s));
+  CUDA_TRY(cudaMemcpyAsync(t->h_res, t->d_res.p, sizeof(ResultBlock), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  int err = 0;
   uint32_t n = 0;
-  CUDA_TRY(cudaMemcpy(&err, t->d_error.p, sizeof err, cudaMemcpyDeviceToHost));
-  if (err) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
+  if (t->h_res->error) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
   CUDA_TRY(cudaMemcpy(&n, t->d_entry_count.p, sizeof n, cudaMemcpyDeviceToHost));
   const int W = pl.W;
   std::vector<uint64_t> keys((size_t)n * W + 1);
@@ -813,9 +918,11 @@ int dtree_destroy(dtree_t *t) {
   if (t->sm_count) {
     DeviceGuard g(t->device);
     t->dev.release_all();
-    t->d_scratch.release(); t->d_wins.release(); t->d_stats.release(); t->d_counter.release(); t->d_error.release();
+    t->d_scratch.release(); t->d_res.release();
     t->d_entry_count.release(); t->d_orders.release();
-    t->d_arena.release(); t->d_locks.release(); t->d_usage.release(); t->d_retry.release();
+    t->d_arena.release(); t->d_locks.release(); t->d_retry.release();
+    if (t->h_res) cudaFreeHost(t->h_res);
+    t->h_res = nullptr;
   }
   delete t;
   return DTREE_OK;
@@ -946,7 +1053,9 @@ static int bind_device(dtree_t *t) {
   if (t->device >= n) return fail(DTREE_ERR_ARG, "device %d does not exist (%d visible)", t->device, n);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, t->device));
-  if (prop.major < 10) return fail(DTREE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", t->device, prop.major, prop.minor);
+  // sm_100a code is not forward compatible: sm_103 / sm_110 / sm_120 devices have no kernel image in this library
+  if (prop.major != 10 || prop.minor != 0)
+    return fail(DTREE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", t->device, prop.major, prop.minor);
   t->sm_count = prop.multiProcessorCount;
   t->smem_optin = prop.sharedMemPerBlockOptin;
   return DTREE_OK;
@@ -958,6 +1067,8 @@ int dtree_sync_device(dtree_t *t) {
   if (rc) return rc;
   DeviceGuard g(t->device);
   if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  begin_call_stats(t);
+  NvtxRange nv("dtree:mirror");
   return ensure_mirror(t, 0);
 }
 
@@ -972,21 +1083,21 @@ int dtree_sample_posterior(dtree_t *t, uint64_t first_election, uint32_t n_elect
                            uint32_t n_winners, int replace, const char *seed, size_t seed_len, uint64_t *win_counts,
                            uint8_t *elim_orders) {
   if (!t || !win_counts) return fail(DTREE_ERR_ARG, "null argument");
+  NvtxRange nv("dtree_sample_posterior");
   int rc = bind_device(t);
   if (rc) return rc;
   DeviceGuard g(t->device);
   if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
   const uint32_t nc = t->tree.P.nc;
-  CUDA_TRY(t->d_wins.reserve(kMaxCandidates));
-  CUDA_TRY(cudaMemsetAsync(t->d_wins.p, 0, kMaxCandidates * sizeof(unsigned long long), 0));
-  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = 0;
-  rc = run_posterior(t, first_election, n_elections, n_ballots, n_winners, replace, seed, seed_len, t->d_wins.p,
-                     elim_orders, 0, true);
+  begin_call_stats(t);
+  rc = ensure_result_block(t);
   if (rc) return rc;
-  unsigned long long w[kMaxCandidates];
-  CUDA_TRY(cudaMemcpy(w, t->d_wins.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  t->stats[kOutD2H] += nc * 8;
-  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = w[c];
+  CUDA_TRY(cudaMemsetAsync(t->d_res.p->wins, 0, sizeof t->d_res.p->wins, 0));
+  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = 0;
+  rc = run_posterior(t, first_election, n_elections, n_ballots, n_winners, replace, seed, seed_len, t->d_res.p->wins,
+                     elim_orders, 0, true);
+  if (rc || n_elections == 0) return rc;
+  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = t->h_res->wins[c];  // came back with the result block
   return DTREE_OK;
 }
 
@@ -998,6 +1109,7 @@ int dtree_sample_posterior_device(dtree_t *t, uint64_t first_election, uint32_t 
   if (rc) return rc;
   DeviceGuard g(t->device);
   if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  begin_call_stats(t);
   return run_posterior(t, first_election, n_elections, n_ballots, n_winners, replace, seed, seed_len,
                        (unsigned long long *)d_win_counts, nullptr, (cudaStream_t)stream, false);
 }
@@ -1007,18 +1119,26 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
                                  const char *seed, size_t seed_len, uint64_t *win_counts) {
   if (!t || !win_counts) return fail(DTREE_ERR_ARG, "null argument");
   if (n_devices < 1 || n_devices > 64) return fail(DTREE_ERR_ARG, "n_devices must be in [1, 64]");
+  NvtxRange nv("dtree_sample_posterior_multi");
   const int visible = dtree_device_count();
   if (visible < 1) return fail(DTREE_ERR_CUDA, "no CUDA device available: libdtree_b200 has no CPU path");
-  const uint32_t nc = t->tree.P.nc;
-  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = 0;
-  // one replica per listed device; index i of `replicas` serves devices[i]
-  while ((int)t->replicas.size() < n_devices) t->replicas.push_back(nullptr);
-  std::vector<dtree *> used;
-  const uint32_t per = (uint32_t)(((uint64_t)n_elections + n_devices - 1) / n_devices);  // ceil, as sharding.py
-  int rc = DTREE_OK;
-  for (int i = 0; i < n_devices && rc == DTREE_OK; ++i) {
+  // every ordinal is checked before anything is launched
+  for (int i = 0; i < n_devices; ++i) {
     const int dev = devices ? devices[i] : i;
     if (dev < 0 || dev >= visible) return fail(DTREE_ERR_ARG, "device %d does not exist (%d visible)", dev, visible);
+  }
+  const uint32_t nc = t->tree.P.nc;
+  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = 0;
+  begin_call_stats(t);
+  // one replica per listed device; index i of `replicas` serves devices[i]
+  while ((int)t->replicas.size() < n_devices) t->replicas.push_back(nullptr);
+  const uint32_t per = (uint32_t)(((uint64_t)n_elections + n_devices - 1) / n_devices);  // ceil, as sharding.py
+  std::vector<Job> jobs;  // the replicas with work, in device-list order
+  jobs.reserve(n_devices);
+  int rc = DTREE_OK;
+  const dtree *sized = nullptr;  // a replica whose arena sizing (pilot) the later ones can take over
+  for (int i = 0; i < n_devices && rc == DTREE_OK; ++i) {
+    const int dev = devices ? devices[i] : i;
     dtree *&r = t->replicas[i];
     if (r && r->device != dev) {
       dtree_destroy(r);
@@ -1042,31 +1162,85 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
     r->urn_max = t->urn_max;
     r->block_threads = t->block_threads;
     r->blocks_per_sm = t->blocks_per_sm;
+    r->arena_cap = t->arena_cap;
+    r->lane_max_splits = t->lane_max_splits;
+    // The abort callback is the parent's: it is polled between waves below, on the calling thread, once for all
+    // devices. A replica only needs to know that its job must be cut into waves.
+    r->should_abort = t->should_abort;
+    r->abort_user = t->abort_user;
     const uint64_t lo = std::min<uint64_t>(n_elections, (uint64_t)i * per), hi = std::min<uint64_t>(n_elections, lo + per);
     if (hi == lo) continue;
     rc = bind_device(r);
     if (rc) break;
     DeviceGuard g(r->device);
-    if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", r->device);
-    CUDA_TRY(r->d_wins.reserve(kMaxCandidates));
-    CUDA_TRY(cudaMemsetAsync(r->d_wins.p, 0, kMaxCandidates * sizeof(unsigned long long), 0));
-    rc = run_posterior(r, first_election + lo, (uint32_t)(hi - lo), n_ballots, n_winners, replace, seed, seed_len,
-                       r->d_wins.p, nullptr, 0, false);
-    used.push_back(r);
+    if (!g.ok) {
+      rc = fail(DTREE_ERR_CUDA, "cannot select device %d", r->device);
+      break;
+    }
+    begin_call_stats(r);
+    rc = ensure_result_block(r);
+    if (rc) break;
+    if (cudaMemsetAsync(r->d_res.p->wins, 0, sizeof r->d_res.p->wins, 0) != cudaSuccess) {
+      rc = fail(DTREE_ERR_CUDA, "clearing win counts on device %d failed", r->device);
+      break;
+    }
+    // Same tree, same parameters, same job shape: the arena sizing measured by the first replica's pilot holds for
+    // all of them, so only that one pilot runs (and the devices are not serialised behind one another's).
+    if (sized && !(r->sizing.valid && r->sizing.version == r->version)) {
+      const dtree::Sizing &z = sized->sizing;
+      r->sizing = z;
+    }
+    jobs.emplace_back();
+    rc = job_prepare(jobs.back(), r, first_election + lo, (uint32_t)(hi - lo), n_ballots, n_winners, replace, seed, seed_len,
+                     r->d_res.p->wins, false, 0);
+    if (rc) {
+      jobs.pop_back();
+      break;
+    }
+    if (!sized && r->sizing.valid) sized = r;
   }
-  // collect (also on failure, so that nothing is left running)
-  for (dtree *r : used) {
+  // waves, round-robin over the devices; the abort callback is polled once per round with every device idle
+  bool more = rc == DTREE_OK;
+  for (uint64_t round = 0; more; ++round) {
+    if (t->should_abort && round > 0) {
+      for (Job &j : jobs) {
+        DeviceGuard g(j.t->device);
+        if (cudaStreamSynchronize(j.s) != cudaSuccess) rc = fail(DTREE_ERR_CUDA, "device %d failed", j.t->device);
+      }
+      if (rc == DTREE_OK && t->should_abort(t->abort_user)) rc = fail(DTREE_ERR_ABORTED, "aborted by the host");
+      if (rc) break;
+    }
+    more = false;
+    for (Job &j : jobs) {
+      if (j.done >= j.n_elections) continue;
+      DeviceGuard g(j.t->device);
+      rc = job_launch_wave(j);
+      if (rc) break;
+      more |= j.done < j.n_elections;
+    }
+    if (rc) break;
+  }
+  // collect — also on failure, so that nothing is left running when the call returns
+  std::string first_error = rc ? g_error : std::string();
+  uint64_t launches = 0;
+  for (Job &j : jobs) {
+    dtree *r = j.t;
     DeviceGuard g(r->device);
-    int rc2 = dtree_sample_posterior_finish(r, nullptr);
-    unsigned long long w[kMaxCandidates];
-    if (rc2 == DTREE_OK && cudaMemcpy(w, r->d_wins.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
-      rc2 = fail(DTREE_ERR_CUDA, "reading win counts from device %d failed", r->device);
-    if (rc2 == DTREE_OK)
-      for (uint32_t c = 0; c < nc; ++c) win_counts[c] += w[c];
-    else if (rc == DTREE_OK)
+    int rc2 = fetch_results(r, j.s);
+    if (rc2 == DTREE_OK && rc == DTREE_OK)
+      for (uint32_t c = 0; c < nc; ++c) win_counts[c] += r->h_res->wins[c];
+    else if (rc == DTREE_OK) {
       rc = rc2;
+      first_error = g_error;
+    }
+    launches += j.launches;
+    for (int k : {kOutEntries, kOutItems, kOutGammas, kOutBinomials, kOutRereads, kOutSlots, kOutUrnItems, kOutArenaRuns,
+                  kOutLaneRetries, kOutH2D, kOutD2H, kOutScratchBytes})
+      t->stats[k] += r->stats[k];
+    t->stats[kOutMode] = r->stats[kOutMode];
   }
-  t->stats[kOutLaunches] = used.size();
+  if (rc) g_error = first_error;
+  t->stats[kOutLaunches] = launches;
   t->stats[kOutElections] = n_elections;
   return rc;
 }
@@ -1076,16 +1250,11 @@ int dtree_sample_posterior_finish(dtree_t *t, void *stream) {
   if (!t->sm_count) return DTREE_OK;
   DeviceGuard g(t->device);
   if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
-  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-  if (!t->d_error.p || !t->d_stats.p) return DTREE_OK;
-  int err = 0;
-  unsigned long long st[kStatCount];
-  CUDA_TRY(cudaMemcpy(&err, t->d_error.p, sizeof err, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(st, t->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
-  if (err) return fail(DTREE_ERR_CUDA, "internal: per-election scratch overflowed");
-  store_kernel_counters(t, st);
-  if (t->stats[kOutMode] >= 1) return absorb_usage(t);
-  return DTREE_OK;
+  if (!t->d_res.p || !t->h_res) {
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return DTREE_OK;
+  }
+  return fetch_results(t, (cudaStream_t)stream);
 }
 
 int dtree_sample_predictive(dtree_t *t, uint32_t n_ballots, const char *seed, size_t seed_len, dtree_ballots_t **out) {
@@ -1230,6 +1399,12 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   } else if (!strcmp(key, "urn_max")) {
     if (value < 0 || value > 8) return fail(DTREE_ERR_ARG, "urn_max must be in [0, 8]");
     t->urn_max = (uint32_t)value;
+  } else if (!strcmp(key, "arena_cap")) {
+    if (value < 0 || value > 0x7FFFFFFF) return fail(DTREE_ERR_ARG, "arena_cap must be >= 0");
+    t->arena_cap = (uint32_t)value;
+  } else if (!strcmp(key, "lane_max_splits")) {
+    if (value < -1) return fail(DTREE_ERR_ARG, "lane_max_splits must be -1 (auto), 0 (no limit) or a positive count");
+    t->lane_max_splits = value;
   } else if (!strcmp(key, "host_build")) {
     t->host_build = value != 0;
     t->mirrored_version = ~0ull;

@@ -33,6 +33,7 @@ struct LaneState {
   uint32_t hw_queue, hw_big;
   uint32_t unresolved;        // ballots (sampled + observed) inside the waiting nodes
   uint32_t rec_w, rec_r;      // 32-byte node records written to / read back from the arena (traffic accounting)
+  uint32_t n_splits;          // waiting nodes split so far (the root not counted)
   bool overflow;
 };
 
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
     const bool active = e < a.n_elections;
     const RngKey key = election_key(a.seed, a.first_election + e);
     LaneState st;
-    st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.n_top = 0; st.eliminated = 0; st.rec_w = 0; st.rec_r = 0; st.hw_live = 0;
+    st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.n_top = 0; st.eliminated = 0; st.rec_w = 0; st.rec_r = 0; st.hw_live = 0; st.n_splits = 0;
 #pragma unroll
     for (uint32_t k = 0; k < kLaneTop; ++k) sh.top_mass[k][tid] = 0;
     st.hw_queue = 0; st.hw_big = 0; st.unresolved = 0; st.overflow = false;
@@ -422,6 +423,8 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
             }
           }
           if (!__any_sync(0xffffffffu, uncertain)) break;
+          if (uncertain && !st.overflow && a.lane_max_splits != 0u && ++st.n_splits > a.lane_max_splits)
+            st.overflow = true;  // a heavy election: a whole warp finishes it faster (replayed by deferred_kernel)
           if (uncertain && !st.overflow) {
             const DItem x = (st.n_top + st.n_big) ? lane_pop_heaviest<BLOCK>(sh, sc, st) : sc.queue[(st.q_head++) % cp.queue];
             st.unresolved -= lane_mass(x);
@@ -442,6 +445,7 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
       if (st.overflow) {
         const uint32_t k = atomicAdd(a.retry_count, 1u);
         if (k < a.retry_cap) a.retry_list[k] = e;
+        if (a.usage) atomicAdd(&a.usage[4], 1u);
       } else {
         const uint32_t standing_mask = ~st.eliminated & cand_mask;
         if (a.elim_orders) {

@@ -58,7 +58,7 @@ struct SimArgs {
   uint32_t n_arenas, arena_cap_items, arena_cap_queue, arena_cap_big;
   unsigned int *arena_locks;   // [n_arenas], 0 = free
   unsigned int *arena_runs;    // number of elections re-run in an arena
-  uint32_t *usage;             // [3] high-water marks: parked pool, work queue, big list
+  uint32_t *usage;             // [0..2] high-water marks: parked pool, work queue, big list; [4] lane_kernel elections handed to the replay
   uint32_t max_warps;          // warps with a larger grid-wide index stay idle (pilot launches)
   // replaying a list of elections (lane_kernel's overflow list): indices relative to first_election
   const uint32_t *election_list;   // NULL: elections 0..n_elections-1
@@ -66,6 +66,7 @@ struct SimArgs {
   uint32_t *retry_list;            // lane_kernel: elections whose arena overflowed
   unsigned int *retry_count;
   uint32_t retry_cap;
+  uint32_t lane_max_splits;        // lane_kernel: an election that needs more node splits goes to the retry list (0: no limit)
   // outputs
   unsigned long long *win_counts;  // [nc], added to
   uint8_t *elim_orders;            // NULL or [n_elections * nc]

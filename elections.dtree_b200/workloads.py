@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 def plackett_luce_ballots(n_candidates, gamma, n, seed, lengths=None):
@@ -37,8 +37,9 @@ def plackett_luce_ballots(n_candidates, gamma, n, seed, lengths=None):
 
 
 def wakehurst():
-    """The reference's only fixture (tests/data/wakehurst2023.soi) as committed under tests/golden/."""
-    with open(os.path.join(_GOLDEN, "wakehurst2023.json")) as f:
+    """The reference's only fixture (tests/data/wakehurst2023.soi), shipped with the package as data/wakehurst2023.json
+    (tests/test_oracle_pin.py checks it against the copy under tests/golden/)."""
+    with open(os.path.join(_DATA, "wakehurst2023.json")) as f:
         return json.load(f)
 
 

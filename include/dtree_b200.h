@@ -187,17 +187,26 @@ int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user
  *      "block_threads" (0 = auto), "blocks_per_sm" (0 = auto), "urn_max" (largest count split by the
  *        Polya-urn shortcut instead of Gamma variates, <= 8);
  *      "host_build" (0 default; 1 = build the tree with the host trie and upload it, the pre-device-build
- *        path, kept to measure against; the two mirrors are identical array for array).
+ *        path, kept to measure against; the two mirrors are identical array for array);
+ *      "arena_cap" (0 default; > 0 = modes 1 and 2 give every election a scratch arena of at most that many node
+ *        records, far too small on purpose, so that tests reach the overflow paths: re-run in a shared worst-case
+ *        arena (mode 1) and hand-over to the replay launch (mode 2); results do not change);
+ *      "lane_max_splits" (-1 default = chosen from the node splits an election typically needs; 0 = no limit;
+ *        n > 0 = in mode 2 an election that needs more than n node splits is handed to the replay launch, where a
+ *        whole warp finishes it, instead of keeping its thread — and the launch — busy; results do not change).
  * Returns DTREE_ERR_ARG for an unknown key. */
 int dtree_set_tuning(dtree_t *t, const char *key, int64_t value);
-/* Statistics of the last sampling call on this handle:
+/* Statistics of the last sampling call on this handle (counters restart at every call; [7] and [14] describe the
+ * scratch and tree build in force):
  *  [0] kernel launches, [1] elections simulated, [2] sampled entries written (mode 0) / 32-byte node records
  *  written to the arenas (modes 1, 2), [3] frontier items
  *  processed, [4] Gamma variates drawn, [5] binomial variates drawn, [6] IRV entry re-reads (mode 0) / node
  *  records read back (modes 1, 2),
  *  [7] device bytes of scratch, [8] H2D bytes, [9] D2H bytes, [10] outcome slots read,
  *  [11] nodes split by the urn shortcut, [12] mode used, [13] elections re-run in a worst-case arena,
- *  [14] kernel launches of the last device tree build. */
+ *  [14] kernel launches of the last device tree build, [15] elections mode 2 handed to its replay launch,
+ *  [16..19] host microseconds spent in the call: device mirror (upload + tree build), planning, enqueueing the
+ *  launches, waiting for and reading back the result. */
 int dtree_last_stats(const dtree_t *t, uint64_t *out, uint32_t cap);
 
 #ifdef __cplusplus
