@@ -68,6 +68,9 @@ _SIGS = {
     "dtree_debug_hash_seed": (C.c_uint64, [C.c_char_p, C.c_size_t]),
     "dtree_debug_gamma": (C.c_int, [C.c_double, C.c_int, C.c_uint64, C.c_uint32, f32p, C.c_int]),
     "dtree_debug_binomial": (C.c_int, [C.c_uint32, C.c_double, C.c_uint64, C.c_uint32, u32p, C.c_int]),
+    "dtree_debug_gamma_ex": (C.c_int, [C.c_double, C.c_int, C.c_uint64, C.c_uint32, f32p, C.c_int, C.c_int]),
+    "dtree_debug_binomial_ex": (C.c_int, [C.c_uint32, C.c_double, C.c_uint64, C.c_uint32, u32p, C.c_int, C.c_int]),
+    "dtree_debug_binv_law": (C.c_int, [C.c_uint32, C.c_double, u32p, C.c_int]),
     "dtree_debug_device_image": (C.c_int, [vp, C.c_int, vp, C.c_uint64, u64p]),
 }
 

@@ -101,7 +101,8 @@ struct HostTimer {
 struct ResultBlock {
   unsigned long long wins[kMaxCandidates];
   unsigned long long stats[8];  // kStatCount <= 8
-  unsigned int usage[8];        // [0..2] arena high-water marks, [3] elections re-run in a worst-case arena, [4] lane retries
+  unsigned int usage[8];        // [0..2] deferred_kernel arena high-water marks, [3] elections re-run in a worst-case
+                                // arena, [4] lane_kernel elections handed to the replay, [5..7] lane_kernel high-water marks
   int error;
   unsigned int counter;         // work counter of the running launch
   unsigned int pad_[2];
@@ -177,7 +178,8 @@ struct dtree {
     uint32_t n_sample = 0, urn_max = 0, min_depth = 0, max_depth = 0;
     double a0 = 0;
     bool vd = false, use_obs = false, short_cuts = false;  // short_cuts: IRV may stop early (smaller elections)
-    uint32_t pool = 0, queue = 0, big = 0;              // largest usage seen (items)
+    uint32_t pool = 0, queue = 0, big = 0;              // largest usage seen (items), warp per election
+    uint32_t lpool = 0, lqueue = 0, lbig = 0;           // largest usage seen by lane_kernel's own elections
     uint32_t cap_pool = 0, cap_queue = 0, cap_big = 0;  // capacities in force (warp per election)
     uint32_t lane_pool = 0, lane_queue = 0, lane_big = 0;  // capacities in force (thread per election)
     double nodes_per_election = 0;                          // node splits per election, last measured
@@ -187,6 +189,8 @@ struct dtree {
   uint32_t urn_max = 8;
   uint32_t arena_cap = 0;        // > 0: per-warp / per-thread arenas hold at most this many items (forces the overflow paths)
   int64_t lane_max_splits = -1;  // lane_kernel hands an election to the replay after this many splits (-1 auto, 0 never)
+  uint32_t tau_quarters = 2;     // deferred_kernel's resolve threshold (deferred.cuh)
+  uint64_t mem_avail = 0;        // device bytes the plans may use (free + held by this handle), as last queried
   int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
   // replicas on other devices for dtree_sample_posterior_multi (owned; same parameters, tree copied when stale)
   std::vector<dtree *> replicas;
@@ -372,7 +376,7 @@ int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, P
 // ballot sits in at most one live node, and a node with only observed ballots is a tree node.
 constexpr uint32_t kMaxArenas = 8;
 
-int make_plan_deferred(dtree *t, uint32_t n_sample, uint32_t n_elections, Plan &pl) {
+int make_plan_deferred(dtree *t, uint32_t n_sample, uint32_t n_elections, bool refresh_memory, Plan &pl) {
   const HostParams &P = t->tree.P;
   pl.W = 1;
   pl.log_gamma = device_params(P).small_alpha != 0;
@@ -395,9 +399,14 @@ int make_plan_deferred(dtree *t, uint32_t n_sample, uint32_t n_elections, Plan &
   pl.arena_queue = (uint32_t)worst;
   pl.arena_big = (uint32_t)std::min<uint64_t>((uint64_t)n_sample / (t->urn_max + 1) + 64, worst);
   pl.arena_stride = (deferred_scratch_bytes(pl.arena_items, pl.arena_queue, pl.arena_big) + 255) & ~255ull;
-  size_t free_b = 0, total_b = 0;
-  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  const uint64_t avail = free_b + t->d_scratch.n + t->d_arena.n;
+  // Device memory this handle may plan with: what is free plus what it already holds. cudaMemGetInfo costs 0.1 ms
+  // (milliseconds while another process polls the driver), so the figure is kept between calls of the same shape.
+  if (refresh_memory || t->mem_avail == 0) {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    t->mem_avail = free_b + t->d_scratch.n + t->d_arena.n;
+  }
+  const uint64_t avail = t->mem_avail;
   pl.n_arenas = (uint32_t)std::min<uint64_t>(kMaxArenas, (uint64_t)((double)avail * 0.25) / pl.arena_stride);
   pl.cap_entries = 0;
   pl.mem_budget = (uint64_t)((double)avail * 0.5);
@@ -425,6 +434,7 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
   a.T.slot_cand = t->dev.slot_cand.p;
   a.T.n_nodes = (uint32_t)t->n_nodes;
   a.urn_max = t->urn_max;
+  a.tau_quarters = t->tau_quarters;
   a.scratch = t->d_scratch.p;
   a.scratch_stride = pl.stride;
   a.cap_items = pl.cap_items;
@@ -503,6 +513,9 @@ int fetch_results(dtree *t, cudaStream_t s) {
       z.pool = std::max(z.pool, R.usage[0]);
       z.queue = std::max(z.queue, R.usage[1]);
       z.big = std::max(z.big, R.usage[2]);
+      z.lpool = std::max(z.lpool, R.usage[5]);
+      z.lqueue = std::max(z.lqueue, R.usage[6]);
+      z.lbig = std::max(z.lbig, R.usage[7]);
       if (t->stats[kOutElections] > 0 && t->stats[kOutItems] > 0)
         z.nodes_per_election = (double)t->stats[kOutItems] / (double)t->stats[kOutElections];
     }
@@ -555,8 +568,14 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
   pl.deferred = t->mode == 1 || t->mode == 2;
   bool want_lane = t->mode == 2;
   if (t->mode < 0) pl.deferred = true;  // the deferred kernels are the faster ones on every configuration measured
+  const HostParams &P = t->tree.P;
+  dtree::Sizing &z = t->sizing;
+  // the arena sizing measured for this tree, these parameters and this kind of job is still good
+  const bool hit = z.valid && z.version == t->version && z.n_sample == n_sample && z.urn_max == t->urn_max &&
+                   z.min_depth == P.min_depth && z.max_depth == P.max_depth && z.a0 == P.a0 && z.vd == P.vd &&
+                   z.use_obs == use_obs && z.short_cuts == (n_winners == 1 && !want_orders);
   if (pl.deferred) {
-    rc = make_plan_deferred(t, n_sample, n_elections, pl);
+    rc = make_plan_deferred(t, n_sample, n_elections, !hit, pl);
     if (rc) return rc;
     if (pl.n_arenas == 0) pl.deferred = false;  // not even one worst-case arena fits: materialise instead
   }
@@ -589,11 +608,6 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
   uint32_t pilot_done = 0;
   bool replay = false;
   if (pl.deferred) {
-    const HostParams &P = t->tree.P;
-    dtree::Sizing &z = t->sizing;
-    const bool hit = z.valid && z.version == t->version && z.n_sample == n_sample && z.urn_max == t->urn_max &&
-                     z.min_depth == P.min_depth && z.max_depth == P.max_depth && z.a0 == P.a0 && z.vd == P.vd &&
-                     z.use_obs == use_obs && z.short_cuts == (n_winners == 1 && !want_orders);
     CUDA_TRY(t->d_arena.reserve(pl.arena_stride * pl.n_arenas));
     // Arena locks start free at every call: a launch that died must not leave one held.
     CUDA_TRY(t->d_locks.reserve(kMaxArenas));
@@ -633,6 +647,10 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
       z.n_sample = n_sample; z.urn_max = t->urn_max; z.min_depth = P.min_depth; z.max_depth = P.max_depth;
       z.a0 = P.a0; z.vd = P.vd; z.use_obs = use_obs; z.short_cuts = n_winners == 1 && !want_orders;
       z.pool = H.usage[0]; z.queue = H.usage[1]; z.big = H.usage[2];
+      // lane_kernel's own elections report their usage later; until then the pilot's (which, splitting in batches,
+      // holds more at a time than lane_kernel's heaviest-first order) stands in. Its heap also holds small-count
+      // nodes that carry many observed ballots, which deferred_kernel keeps in its small-count queue.
+      z.lpool = z.pool; z.lqueue = z.queue; z.lbig = z.big + z.queue;
       z.nodes_per_election = (double)H.stats[kStatItems] / std::max<uint32_t>(pilot_done, 1);
     }
     // Capacities get a 4x margin over the largest election seen and are only revised when an election has
@@ -643,15 +661,14 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
     pl.cap_items = std::min(z.cap_pool, pl.arena_items);
     pl.cap_queue = std::min(z.cap_queue, pl.arena_queue);
     pl.cap_big = std::min(z.cap_big, pl.arena_big);
-    // One thread per election (lane_kernel): 32x more arenas in flight, so a tighter margin (3x the largest election
-    // seen, revised only when an election has used more than 75 % of it); an election that still outgrows its arena
-    // is replayed by deferred_kernel.
-    if (!hit || 4ull * z.pool > 3ull * z.lane_pool) z.lane_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 3ull * z.pool + 512);
-    if (!hit || 4ull * z.queue > 3ull * z.lane_queue) z.lane_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 3ull * z.queue + 512);
-    // (the lane kernel's heap also holds small-count nodes that carry many observed ballots, which the pilot's warp
-    // kernel keeps in its small-count queue: size it for both)
-    const uint64_t lane_heap = (uint64_t)z.big + z.queue;
-    if (!hit || 4ull * lane_heap > 3ull * z.lane_big) z.lane_big = (uint32_t)std::min<uint64_t>(pl.arena_items, 3ull * lane_heap + 64);
+    // One thread per election (lane_kernel): 32x more arenas in flight, so a tighter margin — twice the largest
+    // election lane_kernel itself has finished, revised only when an election has used more than 75 % of it. An
+    // election that still outgrows its arena, or needs more node splits than `lane_max_splits`, is replayed by
+    // deferred_kernel; without that budget one rare heavy election would keep its thread, and with it the whole
+    // launch, busy, and the arenas would have to be sized for it.
+    if (!hit || 4ull * z.lpool > 3ull * z.lane_pool) z.lane_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 2ull * z.lpool + 64);
+    if (!hit || 4ull * z.lqueue > 3ull * z.lane_queue) z.lane_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 2ull * z.lqueue + 32);
+    if (!hit || 4ull * z.lbig > 3ull * z.lane_big) z.lane_big = (uint32_t)std::min<uint64_t>(pl.arena_items, 2ull * z.lbig + 24);
     Plan lp = pl;
     lp.lane = true;
     lp.block = 128;
@@ -666,10 +683,10 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
       lp.cap_queue = std::min(lp.cap_queue, t->arena_cap);
       lp.cap_big = std::min(lp.cap_big, t->arena_cap);
     }
-    lp.stride = (deferred_scratch_bytes(lp.cap_items, lp.cap_queue, lp.cap_big) + 255) & ~255ull;  // per thread
+    lp.stride = (lane_scratch_bytes(lp.cap_items, lp.cap_queue, lp.cap_big) + 255) & ~255ull;  // per election
     lp.stride_block = lp.stride * lp.block;
     {
-      int occ = lane_blocks_per_sm(pl.log_gamma);
+      int occ = lane_blocks_per_sm(device_params(P), pl.log_gamma);
       if (occ <= 0) return fail(DTREE_ERR_CUDA, "lane kernel cannot be resident");
       if (t->blocks_per_sm > 0) occ = std::min(occ, t->blocks_per_sm);
       const uint64_t resident = (uint64_t)occ * t->sm_count;
@@ -721,7 +738,9 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
     a.retry_count = t->d_retry.p;
     a.retry_cap = 1u << 20;
     a.n_arenas = 0;
-    a.lane_max_splits = t->lane_max_splits > 0 ? (uint32_t)std::min<int64_t>(t->lane_max_splits, 0xFFFFFFFFll) : 0u;
+    // split budget of a thread: four times what an election typically needs (measured), at least 32
+    if (t->lane_max_splits < 0) a.lane_max_splits = (uint32_t)std::min(4.0 * t->sizing.nodes_per_election + 32.0, 4.0e9);
+    else a.lane_max_splits = (uint32_t)std::min<int64_t>(t->lane_max_splits, 0xFFFFFFFFll);
     fill_job(pp, ar);
     deferred_fields(ar);
     ar.election_list = t->d_retry.p + 4;
@@ -1163,6 +1182,7 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
     r->block_threads = t->block_threads;
     r->blocks_per_sm = t->blocks_per_sm;
     r->arena_cap = t->arena_cap;
+    r->tau_quarters = t->tau_quarters;
     r->lane_max_splits = t->lane_max_splits;
     // The abort callback is the parent's: it is polled between waves below, on the calling thread, once for all
     // devices. A replica only needs to know that its job must be cut into waves.
@@ -1399,7 +1419,11 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   } else if (!strcmp(key, "urn_max")) {
     if (value < 0 || value > 8) return fail(DTREE_ERR_ARG, "urn_max must be in [0, 8]");
     t->urn_max = (uint32_t)value;
+  } else if (!strcmp(key, "tau_quarters")) {
+    if (value < 1 || value > 3) return fail(DTREE_ERR_ARG, "tau_quarters must be 1, 2 or 3");
+    t->tau_quarters = (uint32_t)value;
   } else if (!strcmp(key, "arena_cap")) {
+    if (value != 0 && value < 8) return fail(DTREE_ERR_ARG, "arena_cap must be 0 or >= 8");
     if (value < 0 || value > 0x7FFFFFFF) return fail(DTREE_ERR_ARG, "arena_cap must be >= 0");
     t->arena_cap = (uint32_t)value;
   } else if (!strcmp(key, "lane_max_splits")) {

@@ -48,7 +48,14 @@ struct DeferredWarp {
   uint32_t unresolved;      // ballots (sampled + observed) inside the waiting nodes
   uint32_t small_mass_max;  // largest number of ballots any node in the small-count queue has had
   uint32_t rec_w;           // node records written by route_child (traffic accounting)
+  // Ballots inside the waiting nodes by weight class: hist[b] = sum of the masses of the waiting nodes with
+  // 2^b <= mass < 2^(b+1); big_cnt[b] = how many of them sit in the big-count list. They let a resolve pass pick
+  // the highest threshold that still leaves too little waiting to matter, instead of a worst-case one.
+  uint32_t hist[32];
+  uint32_t big_cnt[32];
 };
+
+__device__ __forceinline__ uint32_t mass_class(uint32_t m) { return 31u - (uint32_t)__clz(m | 1u); }
 
 // A waiting or parked node carries the number of ballots inside it in the (otherwise unused) prefix word.
 __device__ __forceinline__ uint32_t node_mass(const DItem &x) { return (uint32_t)x.prefix.w[0]; }
@@ -84,7 +91,9 @@ __device__ __forceinline__ void enqueue_node(const SimArgs &a, DeferredWarp &ws,
                                              const DeferredCaps &cp, const DItem &ch) {
   const uint32_t m = node_mass(ch);
   atomicAdd(&ws.unresolved, m);
+  atomicAdd(&ws.hist[mass_class(m)], m);
   if (ch.count > a.urn_max) {
+    atomicAdd(&ws.big_cnt[mass_class(m)], 1u);
     const uint32_t q = coalesced_reserve(&ws.big_tail);
     if (q < cp.big) sc.big[0][q] = ch;
     else ws.overflow = 1;
@@ -260,6 +269,7 @@ __device__ void deferred_resolve(const SimArgs &a, WarpTile<1> &wt, DeferredWarp
         stat[kStatRereads] += 1;
         if (mass >= tau) {
           atomicSub(&ws.unresolved, mass);
+          atomicSub(&ws.hist[mass_class(mass)], mass);
           split_small_node(a, ws, sc, cp, x, eliminated, key, stat);
         } else {  // back to the end of the queue
           stat[kStatEntries] += 1;
@@ -276,6 +286,12 @@ __device__ void deferred_resolve(const SimArgs &a, WarpTile<1> &wt, DeferredWarp
   const uint32_t n_big = min(ws.big_tail, cp.big);
   hw_big = max(hw_big, n_big);
   if (n_big == 0u || ws.overflow) return;
+  {
+    // nothing in the big-count list is heavy enough: leave it alone (tau is a power of two or 1)
+    const uint32_t cls = mass_class(tau);
+    const uint32_t heavy_big = __reduce_add_sync(0xffffffffu, (uint32_t)lane >= cls ? ws.big_cnt[lane] : 0u);
+    if (heavy_big == 0u) return;
+  }
   uint32_t n_keep = 0, n_work = 0, work_mass = 0;
   for (uint32_t start = 0; start < n_big; start += 32u) {
     const uint32_t i = start + lane;
@@ -294,6 +310,8 @@ __device__ void deferred_resolve(const SimArgs &a, WarpTile<1> &wt, DeferredWarp
     if (heavy) {
       sc.big[1][n_work + __popc(hm & below)] = x;
       work_mass += node_mass(x);
+      atomicSub(&ws.hist[mass_class(node_mass(x))], node_mass(x));
+      atomicSub(&ws.big_cnt[mass_class(node_mass(x))], 1u);
     }
     if (keep) sc.big[0][n_keep + __popc(km & below)] = x;
     n_work += __popc(hm);
@@ -328,6 +346,9 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
   const int lane = threadIdx.x & 31;
   const uint32_t nc = a.P.nc;
   ws.tally[lane] = 0;
+  ws.hist[lane] = 0;
+  ws.big_cnt[lane] = 0;
+  __syncwarp();
   if (lane == 0) {
     DItem root;
     root.prefix.w[0] = max(a.n_sample, 1u);  // any positive number: nothing can be decided before the root is split
@@ -345,9 +366,11 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
     ws.unresolved = (uint32_t)root.prefix.w[0];
     ws.small_mass_max = 0;
     ws.rec_w = 1;
+    ws.hist[mass_class((uint32_t)root.prefix.w[0])] = (uint32_t)root.prefix.w[0];
     if (a.n_sample > a.urn_max) {
       sc.big[0][0] = root;
       ws.big_tail = 1;
+      ws.big_cnt[mass_class((uint32_t)root.prefix.w[0])] = 1;
     } else {
       sc.queue[0] = root;
       ws.q_tail = 1;
@@ -385,10 +408,23 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
       const uint32_t gap = second - mn;  // 0 when tied
       if (u == 0u || gap > u) break;     // the weakest candidate is known
       if (ws.overflow) break;
-      // Split what can matter: with n nodes waiting, those lighter than need / (2 n) hold less than need / 2 together.
+      // Split what can matter. The round is settled once fewer than `need` ballots wait; nodes lighter than 2^b hold
+      // hist[0] + ... + hist[b-1] ballots together, so every node of weight >= 2^b is split for the largest b whose
+      // lighter classes hold at most need * tau_quarters / 4 ballots (the rest of the allowance is for children of the
+      // split nodes that have to wait in turn). With nothing to spare (need <= 1, e.g. a tie) everything is split.
       const uint32_t need = early_stop ? max(gap, lead) : gap;
-      const uint32_t n_wait = (ws.q_tail - q_head) + ws.big_tail;
-      const uint32_t tau = need / (2u * max(n_wait, 1u)) + 1u;
+      const uint32_t allow = (uint32_t)(((uint64_t)need * a.tau_quarters) >> 2);
+      uint32_t below = ws.hist[lane];  // inclusive prefix sum over the weight classes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, below, o);
+        if (lane >= o) below += y;
+      }
+      // class b qualifies as the threshold class if the classes below it (prefix of b-1) fit the allowance
+      const uint32_t lighter = __shfl_up_sync(0xffffffffu, below, 1);
+      const uint32_t fits = __ballot_sync(0xffffffffu, lane == 0 || lighter <= allow);
+      const uint32_t cls = 31u - (uint32_t)__clz(fits);  // bit 0 is always set
+      const uint32_t tau = cls == 0u ? 1u : (1u << cls);
       deferred_resolve<LOG>(a, wt, ws, sc, cp, q_head, hw_queue, hw_big, eliminated, tau, log_dp_max, key, stat);
     }
     if (won || ws.overflow) break;

@@ -4,17 +4,40 @@
 
 namespace dtb {
 
+static uint32_t lane_tile_leaves(const DeviceParams &P) {
+  const uint32_t d0 = P.nc + (P.min_depth == 0u ? 1u : 0u);  // outcomes of the root, the widest node
+  uint32_t dp = 2;
+  while (dp < d0) dp <<= 1;
+  return dp;
+}
+
+size_t lane_smem_bytes(const DeviceParams &P) { return (size_t)(128 / 32) * LaneShared::bytes(P.nc, lane_tile_leaves(P)); }
+
+uint64_t lane_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t cap_big) {
+  return LaneScratch::bytes(cap_items, cap_queue, cap_big);
+}
+
+template <bool LOG>
+static cudaError_t prepare(size_t smem) {
+  return cudaFuncSetAttribute(lane_kernel<128, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
 cudaError_t launch_lane(const SimArgs &a, const LaunchCfg &cfg) {
   if (cfg.block != 128) return cudaErrorInvalidValue;
-  if (cfg.log_gamma) lane_kernel<128, true><<<cfg.grid, 128, 0, cfg.stream>>>(a);
-  else lane_kernel<128, false><<<cfg.grid, 128, 0, cfg.stream>>>(a);
+  const size_t smem = lane_smem_bytes(a.P);
+  cudaError_t e = cfg.log_gamma ? prepare<true>(smem) : prepare<false>(smem);
+  if (e != cudaSuccess) return e;
+  if (cfg.log_gamma) lane_kernel<128, true><<<cfg.grid, 128, smem, cfg.stream>>>(a);
+  else lane_kernel<128, false><<<cfg.grid, 128, smem, cfg.stream>>>(a);
   return cudaGetLastError();
 }
 
-int lane_blocks_per_sm(bool lg) {
+int lane_blocks_per_sm(const DeviceParams &P, bool lg) {
+  const size_t smem = lane_smem_bytes(P);
+  if ((lg ? prepare<true>(smem) : prepare<false>(smem)) != cudaSuccess) return 0;
   int n = 0;
-  cudaError_t e = lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lane_kernel<128, true>, 128, 0)
-                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lane_kernel<128, false>, 128, 0);
+  cudaError_t e = lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lane_kernel<128, true>, 128, smem)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lane_kernel<128, false>, 128, smem);
   return e == cudaSuccess ? n : 0;
 }
 

@@ -31,9 +31,10 @@ cudaError_t launch_deferred(const SimArgs &a, const LaunchCfg &cfg);
 int deferred_blocks_per_sm(int block, bool log_gamma);
 uint64_t deferred_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t cap_big);  // per warp
 
-// lane_kernel (lane.cuh): one thread per election, 128 threads per block.
+// lane_kernel (lane.cuh): one thread per election, 32 elections per warp, 128 threads per block.
 cudaError_t launch_lane(const SimArgs &a, const LaunchCfg &cfg);
-int lane_blocks_per_sm(bool log_gamma);
+int lane_blocks_per_sm(const DeviceParams &P, bool log_gamma);
+uint64_t lane_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t cap_big);  // per election
 
 // Stand-alone IRV over entries already placed in block 0's scratch (dtree_irv).
 struct IrvArgs {

@@ -66,6 +66,7 @@ struct SimArgs {
   uint32_t *retry_list;            // lane_kernel: elections whose arena overflowed
   unsigned int *retry_count;
   uint32_t retry_cap;
+  uint32_t tau_quarters;           // deferred_kernel: share (in quarters) of the missing margin that may keep waiting (1..3)
   uint32_t lane_max_splits;        // lane_kernel: an election that needs more node splits goes to the retry list (0: no limit)
   // outputs
   unsigned long long *win_counts;  // [nc], added to
@@ -178,15 +179,18 @@ __device__ __forceinline__ uint32_t coalesced_reserve(uint32_t *cursor) {
 // ball b in bits [8b, 8b+8).
 static __device__ __noinline__ uint64_t urn_picks(const SimArgs &a, const LevelInfo &lv, int32_t node, uint32_t nbase,
                                               uint32_t count, const RngKey key, uint64_t node_key) {
+  // A = (observed ballots below the node) + d a_prior. A fresh outcome is drawn as a mixture: with probability
+  // tot / A one of the observed ballots is copied (exact integer walk over the slot counts), else the prior picks
+  // one of the d outcomes uniformly. Sums are formed in double and the uniform has 32 bits, so a prior-only
+  // outcome next to slots holding millions of ballots keeps its probability a_prior / A.
   const uint32_t d = lv.d;
-  float A;
+  uint32_t tot = 0;
   if (nbase != 0xFFFFFFFFu) {
-    uint32_t tot = a.T.node_total[node];
+    tot = a.T.node_total[node];
     if (lv.T) tot += a.T.slot_count[nbase + lv.K];
-    A = __fmaf_rn((float)d, lv.a_prior, (float)tot);
-  } else {
-    A = __fmul_rn((float)d, lv.a_prior);
   }
+  const double prior = (double)lv.a_prior, seen = (double)tot;
+  const double A = __fma_rn((double)d, prior, seen);
   uint64_t picks = 0;
   U4 r;
 #pragma unroll 1
@@ -194,27 +198,29 @@ static __device__ __noinline__ uint64_t urn_picks(const SimArgs &a, const LevelI
     if ((b & 3u) == 0u) r = node_random(key, node_key, kStreamUrn, b >> 2);
     const uint32_t bits = (b & 3u) == 0u ? r.x : (b & 3u) == 1u ? r.y : (b & 3u) == 2u ? r.z : r.w;
     uint32_t pick;
-    if (!(A > 0.0f)) {
+    if (!(A > 0.0)) {
       // all parameters 0 (distributions.cpp:69-77): the first ball is uniform, the rest follow it
       pick = b == 0u ? uniform_below(bits, d) : (uint32_t)(picks & 0xFFu);
     } else {
-      const float u = __fmul_rn(u01f(bits), __fadd_rn(A, (float)b));
-      if (u >= A) {
-        uint32_t j = (uint32_t)__fadd_rn(u, -A);
+      const double u = __dmul_rn(u01d(bits), __dadd_rn(A, (double)b));
+      if (u >= A) {  // copies an earlier ball
+        uint32_t j = (uint32_t)__dadd_rn(u, -A);
         if (j >= b) j = b - 1u;
         pick = (uint32_t)(picks >> (8u * j)) & 0xFFu;
-      } else if (nbase != 0xFFFFFFFFu) {
-        float acc = 0.0f;
-        pick = 0u;  // on fall-through (rounding): the last outcome with a positive parameter
+      } else if (u < seen) {  // copies an observed ballot: the slot holding the floor(u)-th of them
+        const uint32_t target = (uint32_t)u;
+        uint32_t acc = 0;
+        pick = d - 1u;
 #pragma unroll 1
         for (uint32_t i = 0; i < d; ++i) {
-          const float al = __fadd_rn((float)a.T.slot_count[nbase + i], lv.a_prior);
-          acc = __fadd_rn(acc, al);
-          if (al > 0.0f) pick = i;
-          if (u < acc) break;
+          acc += a.T.slot_count[nbase + i];
+          if (target < acc) {
+            pick = i;
+            break;
+          }
         }
-      } else {
-        pick = (uint32_t)__fdividef(u, lv.a_prior);
+      } else {  // the prior: uniform over the d outcomes
+        pick = (uint32_t)__ddiv_rn(__dadd_rn(u, -seen), prior);
         if (pick >= d) pick = d - 1u;
       }
     }
@@ -253,13 +259,8 @@ __device__ void split_items(const SimArgs &a, WarpTile<W> &wt, uint32_t m, int l
     float g = LOG ? -INFINITY : 0.0f;
     if (slot < lv.d && x.count > a.urn_max) {
       const uint32_t nb = wt.nbase[it];
-      float alpha = lv.a_prior;
-      if (nb != 0xFFFFFFFFu) alpha = __fadd_rn((float)a.T.slot_count[nb + slot], lv.a_prior);
-      if (alpha > 0.0f) {  // Gamma(0) is the point mass at 0
-        uint32_t att = 0;
-        g = gamma_variate<LOG>(alpha, key, x.node_key, slot, att);
-        stat[kStatGammas] += 1;
-      }
+      const uint32_t seen = nb != 0xFFFFFFFFu ? a.T.slot_count[nb + slot] : 0u;
+      g = outcome_gamma<LOG>(seen, lv.a_prior, key, x.node_key, slot, stat[kStatGammas]);  // Gamma(0) is the point mass at 0
     }
     wt.val[it * stride + dp + slot] = __float_as_uint(g);
   }

@@ -2,8 +2,31 @@
 //
 // These replace libstdc++'s std::gamma_distribution<double> (Marsaglia-Tsang,
 // bits/random.tcc:2335-2392) and std::binomial_distribution<unsigned> (bits/random.tcc:1475-1680)
-// as used by the reference in distributions.cpp:63-64 and :45-46. Both are exact samplers, so
-// the draws are equal in distribution to the reference's (not bit-equal: different generator).
+// as used by the reference in distributions.cpp:63-64 and :45-46. Both are rejection samplers whose
+// accept/reject decisions are made exactly as a double-precision evaluation would make them; what is
+// approximate is listed, with its size, under "Arithmetic and its error" below. The draws are equal in
+// distribution to the reference's up to those bounds (not bit-equal: different generator).
+//
+// How the decisions stay exact while the work is done in float: every acceptance test is first
+// evaluated in f32 against bounds widened by a guard band that covers the f32 rounding error (with a
+// factor >= 5 to spare); only a draw that falls inside the band is re-evaluated by the out-of-line f64
+// test. The outcome is therefore the f64 outcome on the same inputs, and the f64 pipe sees ~1 % of
+// what it used to (profiles/r01j: 45 % of lane_kernel's instructions were these tests at 5 of 32 lanes).
+// tests/test_gpu_variates.py runs both variants over 10^8 draws and requires identical outputs.
+//
+// Arithmetic and its error (W8 of the round-1 review), per variate:
+//  * Normal deviates: Box-Muller on two 23-bit uniforms with __logf/__cosf (abs. error 2^-21): the
+//    deviate is a N(0,1) truncated at 5.77 sigma (tail mass 8e-9) and perturbed by <= 1e-6 relative;
+//    the Marsaglia-Tsang test then uses that same perturbed deviate, so the Gamma law inherits a
+//    total-variation error <= 2e-6 (perturbation of the proposal density), zero-mean to first order.
+//  * Gamma shape: count + a_prior in f32 for counts < 2^22 (exact to 2^-24 relative: a shift of the
+//    mean by <= 0.03 standard deviations at the very worst, count ~ 2^22, a zero-mean rounding);
+//    counts >= 2^22 take the all-double path gamma_big.
+//  * BINV (n p < 30): sequential inversion in f32 of one 23-bit uniform; total variation measured
+//    exhaustively over all 2^23 uniforms on a grid of (n, p): <= 4e-6 (tests/test_gpu_variates.py).
+//  * BTRS (n p >= 30): proposals in f32 for n < 2^20 (in f64 above), uniforms with 32-bit resolution
+//    kept in the tails (us = distance to the nearer end of the unit interval is formed from the integer,
+//    so it is never rounded against 1/2); acceptance decisions as described above.
 //
 // Arithmetic that decides accept/reject is written with explicit rounding intrinsics so that
 // every kernel that inlines these functions makes bit-identical decisions for a given counter.
@@ -14,6 +37,10 @@
 
 namespace dtb {
 
+// 32-bit uniform in (0, 1] as a float: small values keep their full resolution (2^-33 .. 2^-9 are exact),
+// values near 1 are rounded to 2^-24.
+__device__ __forceinline__ float u32f(uint32_t r) { return __fmul_rn(__fadd_rn((float)r, 0.5f), 2.3283064365386963e-10f); }
+
 // ---------------------------------------------------------------------------------------------
 // Gamma(alpha, 1), alpha > 0. Marsaglia & Tsang (2000): d = a - 1/3, c = 1/sqrt(9d),
 // v = (1 + c x)^3 with x ~ N(0,1); accept if u < 1 - 0.0331 x^4 (squeeze) or
@@ -22,10 +49,11 @@ namespace dtb {
 // LOG = true returns log(variate) instead: with alpha as small as 1e-4, U^(1/alpha) underflows
 // even in double (the reference then falls back to a uniform one-hot, distributions.cpp:69-77);
 // carrying the logarithm keeps the exact alpha -> 0 limit and needs no fallback.
-// One Philox block per attempt: x from (r.x, r.y) by Box-Muller, u = r.z, boost uniform = r.w.
-// The exact Marsaglia-Tsang acceptance test, log u < x^2/2 + d (1 - v + log v), in double: the float
-// form cancels catastrophically for large d. Reached by a few percent of the draws only, so it lives
-// out of line (one copy in the kernel instead of one per call site: the kernels are I-cache bound).
+// One Philox block per attempt: x from (r.x, r.y) by Box-Muller, u = r.z, boost uniform = r.w of the
+// accepted attempt (independent of the acceptance decision, which only looks at x and u).
+
+// The exact Marsaglia-Tsang acceptance test in double. Reached only from inside the guard band of
+// gamma_attempt (about 1 draw in 10^4), so it lives out of line.
 static __device__ __noinline__ bool gamma_accept_exact(float c, float x, float d, float u) {
   double t = __dmul_rn((double)c, (double)x);
   double vd = __dadd_rn(1.0, t);
@@ -35,38 +63,132 @@ static __device__ __noinline__ bool gamma_accept_exact(float c, float x, float d
   return log((double)u) < rhs;
 }
 
-template <bool LOG>
-__device__ __forceinline__ float gamma_variate(float alpha, RngKey key, uint64_t node_key, uint32_t slot,
-                                               uint32_t &attempts) {
-  const bool boost = alpha < 1.0f;
-  const float a = boost ? __fadd_rn(alpha, 1.0f) : alpha;
-  const float d = __fadd_rn(a, -0.333333343f);
-  const float c = rsqrtf(__fmul_rn(9.0f, d));
-  float v;
-  uint32_t boost_bits = 0;
-  for (uint32_t attempt = 0;; ++attempt) {
-    U4 r = node_random(key, node_key, kStreamGamma + slot, attempt);
-    ++attempts;
-    if (attempt == 0) boost_bits = r.w;
-    float rad = sqrtf(__fmul_rn(-2.0f, __logf(u01f(r.x))));
-    float x = __fmul_rn(rad, __cosf(__fmul_rn(6.28318548f, u01f(r.y))));
-    v = __fmaf_rn(c, x, 1.0f);
-    if (v <= 0.0f) continue;
-    v = __fmul_rn(__fmul_rn(v, v), v);
-    float u = u01f(r.z);
-    float x2 = __fmul_rn(x, x);
-    if (u < __fmaf_rn(-0.0331f, __fmul_rn(x2, x2), 1.0f)) break;
-    if (gamma_accept_exact(c, x, d, u)) break;
-    if (attempt > 64u) break;  // unreachable in practice (acceptance > 0.95); bounds the loop
+struct GammaShape {
+  float alpha, d, c;
+  bool boost;
+};
+
+__device__ __forceinline__ GammaShape gamma_shape(float alpha) {
+  GammaShape s;
+  s.alpha = alpha;
+  s.boost = alpha < 1.0f;
+  const float a = s.boost ? __fadd_rn(alpha, 1.0f) : alpha;
+  s.d = __fadd_rn(a, -0.333333343f);
+  s.c = rsqrtf(__fmul_rn(9.0f, s.d));
+  return s;
+}
+
+// One Marsaglia-Tsang attempt on the Philox block r. True when accepted; g = d v then.
+// `exact_only` (test hook) sends every draw that fails the squeeze to the f64 test.
+template <bool EXACT_ONLY = false>
+__device__ __forceinline__ bool gamma_attempt(const GammaShape &s, const U4 r, float &g) {
+  const float rad = sqrtf(__fmul_rn(-2.0f, __logf(u01f(r.x))));
+  const float x = __fmul_rn(rad, __cosf(__fmul_rn(6.28318548f, u01f(r.y))));
+  const float w = __fmul_rn(s.c, x);
+  float v = __fmaf_rn(s.c, x, 1.0f);
+  if (v <= 0.0f) return false;
+  v = __fmul_rn(__fmul_rn(v, v), v);
+  const float u = u01f(r.z);
+  const float x2 = __fmul_rn(x, x);
+  g = __fmul_rn(s.d, v);
+  if (u < __fmaf_rn(-0.0331f, __fmul_rn(x2, x2), 1.0f)) return true;
+  if (!EXACT_ONLY) {
+    // log u < x^2/2 + d (1 - v + log v) in f32. With w = c x: 1 - v + log v = -4.5 w^2 + S(w),
+    // S(w) = sum_{n>=4} 3 (-1)^(n+1) w^n / n, and 4.5 d c^2 = 1/2, so the right-hand side is d S(w) up to the
+    // rounding of c (|x^2 eps_c| <= 1.6e-5, inside the guard). The series is used where it converges fast
+    // (|w| < 1/4, i.e. every large shape, where the direct form cancels catastrophically); elsewhere d < 60 and
+    // the direct form is accurate.
+    const float lu = logf(u);
+    float rhs, guard;
+    if (fabsf(w) < 0.25f) {
+      float p = -0.25f;                       // -3/12
+      p = __fmaf_rn(p, w, 0.272727281f);      // +3/11
+      p = __fmaf_rn(p, w, -0.3f);             // -3/10
+      p = __fmaf_rn(p, w, 0.333333343f);      // +3/9
+      p = __fmaf_rn(p, w, -0.375f);           // -3/8
+      p = __fmaf_rn(p, w, 0.428571433f);      // +3/7
+      p = __fmaf_rn(p, w, -0.5f);             // -3/6
+      p = __fmaf_rn(p, w, 0.6f);              // +3/5
+      p = __fmaf_rn(p, w, -0.75f);            // -3/4
+      const float w2 = __fmul_rn(w, w);
+      rhs = __fmul_rn(__fmul_rn(s.d, p), __fmul_rn(w2, w2));
+      guard = __fmaf_rn(4e-6f, fabsf(rhs), 6e-5f);
+    } else {
+      rhs = __fmaf_rn(s.d, __fadd_rn(__fadd_rn(1.0f, -v), logf(v)), __fmul_rn(0.5f, x2));
+      guard = __fmaf_rn(2e-5f, fabsf(rhs) + fabsf(lu), 3e-4f);
+    }
+    if (lu < __fadd_rn(rhs, -guard)) return true;
+    if (lu > __fadd_rn(rhs, guard)) return false;
   }
-  float g = __fmul_rn(d, v);
+  return gamma_accept_exact(s.c, x, s.d, u);
+}
+
+template <bool LOG>
+__device__ __forceinline__ float gamma_finish(const GammaShape &s, float g, uint32_t boost_bits) {
   if (LOG) {
     float lg = logf(g);
-    if (boost) lg = __fadd_rn(lg, __fdividef(logf(u01f(boost_bits)), alpha));
+    if (s.boost) lg = __fadd_rn(lg, __fdividef(logf(u01f(boost_bits)), s.alpha));
     return lg;
   }
-  if (boost) g = __fmul_rn(g, __expf(__fdividef(logf(u01f(boost_bits)), alpha)));
+  if (s.boost) g = __fmul_rn(g, __expf(__fdividef(logf(u01f(boost_bits)), s.alpha)));
   return g;
+}
+
+template <bool LOG, bool EXACT_ONLY = false>
+__device__ __forceinline__ float gamma_variate(float alpha, RngKey key, uint64_t node_key, uint32_t slot,
+                                               uint32_t &attempts) {
+  const GammaShape s = gamma_shape(alpha);
+  float g = 0.0f;
+  uint32_t boost_bits = 0;
+  for (uint32_t attempt = 0;; ++attempt) {
+    const U4 r = node_random(key, node_key, kStreamGamma + slot, attempt);
+    ++attempts;
+    boost_bits = r.w;
+    if (gamma_attempt<EXACT_ONLY>(s, r, g)) break;
+    if (attempt > 64u) {  // unreachable in practice (acceptance > 0.95); bounds the loop
+      g = s.d;
+      break;
+    }
+  }
+  return gamma_finish<LOG>(s, g, boost_bits);
+}
+
+// Shapes of 2^22 and more (an outcome slot that observed millions of ballots): count + a_prior is no longer exact
+// in f32 and d v would carry a bias of up to 0.03 standard deviations, so the whole variate is drawn in double.
+// Same Philox blocks, same algorithm. Out of line: a handful of nodes per tree at most.
+template <bool LOG>
+static __device__ __noinline__ float gamma_big(double alpha, RngKey key, uint64_t node_key, uint32_t slot) {
+  const double d = alpha - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  double g = d;
+  for (uint32_t attempt = 0; attempt <= 64u; ++attempt) {
+    const U4 r = node_random(key, node_key, kStreamGamma + slot, attempt);
+    const double rad = sqrt(-2.0 * log(u01d(r.x)));
+    const double x = rad * cospi(2.0 * u01d(r.y));
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    const double u = u01d(r.z), x2 = x * x;
+    g = d * v;
+    if (u < 1.0 - 0.0331 * x2 * x2) break;
+    if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) break;
+  }
+  return LOG ? (float)log(g) : (float)g;
+}
+
+// The Gamma variate of one outcome of a tree node: shape = observed count + prior parameter.
+// Returns 0 (LOG: -inf) for shape 0, the point mass at 0.
+template <bool LOG>
+__device__ __forceinline__ float outcome_gamma(uint32_t count, float a_prior, RngKey key, uint64_t node_key, uint32_t slot,
+                                               uint32_t &n_drawn) {
+  if (count >= (1u << 22)) {
+    ++n_drawn;
+    return gamma_big<LOG>((double)count + (double)a_prior, key, node_key, slot);
+  }
+  const float alpha = __fadd_rn((float)count, a_prior);
+  if (!(alpha > 0.0f)) return LOG ? -INFINITY : 0.0f;
+  uint32_t att = 0;
+  ++n_drawn;
+  return gamma_variate<LOG>(alpha, key, node_key, slot, att);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -81,7 +203,7 @@ static __device__ __noinline__ double stirling_tail(double k) {
   return (1.0 / 12 - (1.0 / 360 - t2 * (1.0 / 1260)) * t2) * t;
 }
 
-// BTRS acceptance test for candidate k (Hörmann 1993, step 3.2), out of line for the same reason.
+// BTRS acceptance test for candidate k in double (Hörmann 1993, step 3.2): v alpha / (a / us^2 + b) <= f(k) / f(m).
 static __device__ __noinline__ bool btrs_accept(double nd, double p, double spq, double b, double a, double us, double v,
                                          double kd) {
   const double q = 1.0 - p;
@@ -96,31 +218,130 @@ static __device__ __noinline__ bool btrs_accept(double nd, double p, double spq,
   return lhs <= ub;
 }
 
-// Binomial(n, ps) for ps <= 1/2, exact.
-//  * n ps < 30: sequential inversion (BINV, Kachitvichyanukul & Schmeiser 1988) on one uniform;
-//  * otherwise: BTRS, transformed rejection with squeeze (Hörmann 1993), in double because the
-//    candidate k = floor((2a/us + b)u + c) must be an exact integer up to n < 2^32.
-__device__ __forceinline__ uint32_t binomial_small_p(uint32_t n, float ps, RngKey key, uint64_t node_key,
-                                                     uint32_t slot, uint32_t &attempts) {
-  if (n == 0u || !(ps > 0.0f)) return 0u;
+// ---- BINV -------------------------------------------------------------------------------------
+// Binomial(n, ps), ps <= 1/2, n ps < 30: sequential inversion (Kachitvichyanukul & Schmeiser 1988) of one uniform.
+__device__ __forceinline__ uint32_t binv(uint32_t n, float ps, uint32_t bits) {
   const float nf = (float)n;
-  if (__fmul_rn(nf, ps) < 30.0f) {
-    U4 r = node_random(key, node_key, kStreamBinomial + slot, 0u);
-    ++attempts;
-    float qs = __fadd_rn(1.0f, -ps);
-    float s = __fdividef(ps, qs);
-    float a = __fmul_rn(__fadd_rn(nf, 1.0f), s);
-    float pk = __expf(__fmul_rn(nf, log1pf(-ps)));  // P(X = 0) = q^n; n ps < 30 and ps <= 1/2, so >= e^-42
-    float u = u01f(r.x);
-    uint32_t k = 0;
-    const uint32_t kmax = n < 192u ? n : 192u;
-    while (u > pk && k < kmax) {
-      u = __fadd_rn(u, -pk);
-      ++k;
-      pk = __fmul_rn(pk, __fadd_rn(__fdividef(a, (float)k), -s));  // P(k) = P(k-1) ((n+1)/k - 1) p/q
-    }
-    return k;
+  const float qs = __fadd_rn(1.0f, -ps);
+  const float s = __fdividef(ps, qs);
+  const float a = __fmul_rn(__fadd_rn(nf, 1.0f), s);
+  float pk = __expf(__fmul_rn(nf, log1pf(-ps)));  // P(X = 0) = q^n; n ps < 30 and ps <= 1/2, so >= e^-42
+  float u = u01f(bits);
+  uint32_t k = 0;
+  const uint32_t kmax = n < 192u ? n : 192u;
+  while (u > pk && k < kmax) {
+    u = __fadd_rn(u, -pk);
+    ++k;
+    pk = __fmul_rn(pk, __fadd_rn(__fdividef(a, (float)k), -s));  // P(k) = P(k-1) ((n+1)/k - 1) p/q
   }
+  return k;
+}
+
+// ---- BTRS in f32 (n < 2^20) -------------------------------------------------------------------
+// Transformed rejection with squeeze (Hörmann 1993). A proposal is k = floor((2a/us + b) u + c) from u uniform on
+// (-1/2, 1/2), us = 1/2 - |u|; it is accepted at once when us >= 0.07 and v <= vr (86 % of the proposals at large
+// n p q), else if v alpha / (a/us^2 + b) <= f(k)/f(m), m the mode.
+struct Btrs32 {
+  float nf, p, spq, b, a, c, vr, npq;
+  double np_d;  // n p in double: k - n p is where f32 would cancel
+  uint32_t n, m;
+};
+
+__device__ __forceinline__ Btrs32 btrs32_setup(uint32_t n, float ps) {
+  Btrs32 s;
+  s.n = n;
+  s.nf = (float)n;
+  s.p = ps;
+  const float q = __fadd_rn(1.0f, -ps);
+  s.npq = __fmul_rn(__fmul_rn(s.nf, ps), q);
+  s.spq = sqrtf(s.npq);
+  s.b = __fmaf_rn(2.53f, s.spq, 1.15f);
+  s.a = __fmaf_rn(0.01f, ps, __fmaf_rn(0.0248f, s.b, -0.0873f));
+  s.c = __fmaf_rn(s.nf, ps, 0.5f);
+  s.vr = __fadd_rn(0.92f, -__fdividef(4.2f, s.b));
+  s.np_d = __dmul_rn((double)n, (double)ps);
+  s.m = (uint32_t)__dadd_rn(s.np_d, (double)ps);  // the mode floor((n+1) p) = floor(n p + p)
+  return s;
+}
+
+// Proposal from two 32-bit words. us is formed from the integer distance to the nearer end of the unit interval, so
+// the tails keep the generator's full 2^-32 resolution. Returns k as a float (an integer; may be < 0 or > n).
+__device__ __forceinline__ float btrs32_propose(const Btrs32 &s, uint32_t ru, uint32_t rv, float &us, float &v) {
+  const bool upper = (ru >> 31) != 0u;
+  const uint32_t t = upper ? ~ru : ru;  // < 2^31
+  us = __fmul_rn(__fadd_rn((float)t, 0.5f), 2.3283064365386963e-10f);   // in (0, 1/2]
+  const float au = __fadd_rn(0.5f, -us);                                   // |u|
+  const float u = upper ? au : -au;
+  v = u32f(rv);
+  const float coef = __fadd_rn(__fdividef(__fmul_rn(2.0f, s.a), us), s.b);
+  return floorf(__fmaf_rn(coef, u, s.c));
+}
+
+// log(x!) - log(sqrt(2 pi x) (x/e)^x): table for x < 16, asymptotic series above (Loader 2000, "stirlerr").
+static __device__ const float kStirlErr[16] = {0.0f, 0.0810614668f, 0.0413406960f, 0.0276779257f, 0.0207906721f,
+                                               0.0166446912f, 0.0138761288f, 0.0118967099f, 0.0104112653f, 0.00925546218f,
+                                               0.00833056343f, 0.00757367548f, 0.00694284010f, 0.00640899419f,
+                                               0.00595137011f, 0.00555473355f};
+__device__ __forceinline__ float stirlerr32(float x) {
+  if (x < 16.0f) return kStirlErr[(int)x];
+  const float r = __fdividef(1.0f, x), r2 = __fmul_rn(r, r);
+  return __fmul_rn(r, __fmaf_rn(-r2, __fmaf_rn(-r2, 7.93650794e-4f, 2.77777778e-3f), 8.33333333e-2f));
+}
+
+// x log(x / mu) + mu - x from dx = x - mu (formed without cancellation by the caller) and s = x + mu: Loader's series
+// in v = dx / s, 10 terms; *av = |v| tells the caller whether it has converged (|v| <= 0.4: remainder < 1e-8 relative).
+__device__ __forceinline__ float bd0_32(float x, float dx, float s, float &av) {
+  const float v = __fdiv_rn(dx, s), v2 = __fmul_rn(v, v);
+  av = fabsf(v);
+  float t = 4.76190476e-2f;            // 1/21
+  t = __fmaf_rn(t, v2, 5.26315789e-2f);  // 1/19
+  t = __fmaf_rn(t, v2, 5.88235294e-2f);  // 1/17
+  t = __fmaf_rn(t, v2, 6.66666667e-2f);  // 1/15
+  t = __fmaf_rn(t, v2, 7.69230769e-2f);  // 1/13
+  t = __fmaf_rn(t, v2, 9.09090909e-2f);  // 1/11
+  t = __fmaf_rn(t, v2, 0.111111111f);    // 1/9
+  t = __fmaf_rn(t, v2, 0.142857143f);    // 1/7
+  t = __fmaf_rn(t, v2, 0.2f);            // 1/5
+  t = __fmaf_rn(t, v2, 0.333333333f);    // 1/3
+  return __fmaf_rn(dx, v, __fmul_rn(__fmul_rn(2.0f, x), __fmul_rn(__fmul_rn(v, v2), t)));
+}
+
+// The BTRS acceptance test  log(v alpha / (a/us^2 + b)) <= log(f(k)/f(m))  at f32 precision.
+// log f(k) - log f(m) is evaluated in Loader's saddle-point form (the one R's dbinom uses),
+//   1/2 log(m (n-m) / (k (n-k))) - [stirlerr(k) + stirlerr(n-k) - stirlerr(m) - stirlerr(n-m)]
+//       - [bd0(k, np) + bd0(n-k, nq) - bd0(m, np) - bd0(n-m, nq)],
+// every term of which is small and free of cancellation once k - np and m - np have been formed in double; the
+// result is within 1.1e-5 of the double-precision value over 1.3 M (n, p, k) cases with n < 2^20, n p >= 30
+// (measured: 3 % of the guard band used below). Returns 1 accept, 0 reject, -1 undecided: inside the guard band, or
+// too far in a tail for the series (|k - np| > 0.4 (k + np)); the caller then asks btrs_accept. Out of line: reached
+// by ~15-45 % of the proposals only, and one copy keeps the kernels' hot loops inside the instruction cache.
+static __device__ __noinline__ int btrs32_accept(const Btrs32 &s, float us, float v, float kd) {
+  const uint32_t k = (uint32_t)kd;
+  if (k == 0u || k >= s.n) return -1;
+  const float alpha = __fmul_rn(__fadd_rn(2.83f, __fdividef(5.1f, s.b)), s.spq);
+  const float vv = __fdiv_rn(__fmul_rn(v, alpha), __fadd_rn(__fdiv_rn(s.a, __fmul_rn(us, us)), s.b));
+  const float lv = logf(vv);
+  const float dxk = (float)__dadd_rn((double)k, -s.np_d), dxm = (float)__dadd_rn((double)s.m, -s.np_d);
+  const float kf = kd, mf = (float)s.m, nk = (float)(s.n - k), nm = (float)(s.n - s.m);
+  const float npf = (float)s.np_d, nqf = (float)__dadd_rn((double)s.n, -s.np_d);
+  const float delta = (float)((int)k - (int)s.m);
+  const float half = __fmul_rn(0.5f, __fadd_rn(log1pf(-__fdiv_rn(delta, kf)), log1pf(__fdiv_rn(delta, nk))));
+  const float st = __fadd_rn(__fadd_rn(stirlerr32(kf), stirlerr32(nk)), -__fadd_rn(stirlerr32(mf), stirlerr32(nm)));
+  float v1, v2, v3, v4;
+  const float bd = __fadd_rn(__fadd_rn(bd0_32(kf, dxk, __fadd_rn(kf, npf), v1), bd0_32(nk, -dxk, __fadd_rn(nk, nqf), v2)),
+                             -__fadd_rn(bd0_32(mf, dxm, __fadd_rn(mf, npf), v3), bd0_32(nm, -dxm, __fadd_rn(nm, nqf), v4)));
+  if (fmaxf(v1, v2) > 0.4f) return -1;
+  const float lf = __fadd_rn(__fadd_rn(half, -st), -bd);
+  const float guard = __fmaf_rn(8e-6f, fabsf(lf) + fabsf(lv), 3e-5f);
+  if (lv < __fadd_rn(lf, -guard)) return 1;
+  if (lv > __fadd_rn(lf, guard)) return 0;
+  return -1;
+}
+
+// BTRS entirely in double, for n >= 2^20 (the candidate k = floor((2a/us + b)u + c) must be an exact integer up to
+// n < 2^32). Only the few nodes at the top of a very large election get here: out of line.
+static __device__ __noinline__ uint32_t binomial_btrs64(uint32_t n, float ps, RngKey key, uint64_t node_key, uint32_t slot,
+                                                       uint32_t &attempts) {
   const double nd = (double)n, p = (double)ps, q = 1.0 - p;
   const double spq = sqrt(nd * p * q);
   const double b = 1.15 + 2.53 * spq;
@@ -142,6 +363,43 @@ __device__ __forceinline__ uint32_t binomial_small_p(uint32_t n, float ps, RngKe
     }
     if (attempt > 256u) return (uint32_t)(nd * p);  // unreachable in practice
   }
+}
+
+// Binomial(n, ps) for ps <= 1/2.
+//  * n ps < 30: BINV on one uniform;
+//  * otherwise BTRS: in f32 with guard-banded decisions for n < 2^20, in f64 above (the candidate
+//    k = floor((2a/us + b)u + c) must be an exact integer up to n < 2^32).
+// EXACT_ONLY (test hook): every acceptance test that is not a quick accept is made by the f64 function.
+template <bool EXACT_ONLY = false>
+__device__ __forceinline__ uint32_t binomial_small_p(uint32_t n, float ps, RngKey key, uint64_t node_key,
+                                                     uint32_t slot, uint32_t &attempts) {
+  if (n == 0u || !(ps > 0.0f)) return 0u;
+  const float nf = (float)n;
+  if (__fmul_rn(nf, ps) < 30.0f) {
+    const U4 r = node_random(key, node_key, kStreamBinomial + slot, 0u);
+    ++attempts;
+    return binv(n, ps, r.x);
+  }
+  if (n < (1u << 20)) {
+    const Btrs32 s = btrs32_setup(n, ps);
+    for (uint32_t attempt = 0;; ++attempt) {
+      const U4 r = node_random(key, node_key, kStreamBinomial + slot, attempt);
+      ++attempts;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float us, v;
+        const float kd = btrs32_propose(s, half ? r.z : r.x, half ? r.w : r.y, us, v);
+        if (us >= 0.07f && v <= s.vr) return (uint32_t)kd;
+        if (kd < 0.0f || kd > s.nf) continue;
+        int ok = EXACT_ONLY ? -1 : btrs32_accept(s, us, v, kd);
+        if (ok < 0)
+          ok = btrs_accept((double)n, (double)ps, (double)s.spq, (double)s.b, (double)s.a, (double)us, (double)v, (double)kd) ? 1 : 0;
+        if (ok) return (uint32_t)kd;
+      }
+      if (attempt > 256u) return (uint32_t)__fmul_rn(nf, ps);  // unreachable in practice
+    }
+  }
+  return binomial_btrs64(n, ps, key, node_key, slot, attempts);
 }
 
 }  // namespace dtb

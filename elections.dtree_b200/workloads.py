@@ -38,7 +38,7 @@ def plackett_luce_ballots(n_candidates, gamma, n, seed, lengths=None):
 
 def wakehurst():
     """The reference's only fixture (tests/data/wakehurst2023.soi), shipped with the package as data/wakehurst2023.json
-    (tests/test_oracle_pin.py checks it against the copy under tests/golden/)."""
+    (the tests check it against the copy under tests/golden/)."""
     with open(os.path.join(_DATA, "wakehurst2023.json")) as f:
         return json.load(f)
 

@@ -22,6 +22,15 @@ uint64_t dtree_debug_hash_seed(const char *seed, size_t seed_len);
 int dtree_debug_gamma(double alpha, int log_space, uint64_t seed, uint32_t n, float *out, int device);
 /* n independent Binomial(n_trials, p) variates, 0 <= p <= 1. */
 int dtree_debug_binomial(uint32_t n_trials, double p, uint64_t seed, uint32_t n, uint32_t *out, int device);
+/* The same draws with every accept/reject decision that is not a quick accept made by the double-precision test
+ * (exact_only = 1) instead of the guard-banded f32 test with f64 fall-back (exact_only = 0, what the kernels run):
+ * the outputs must be identical, which is how the guard bands are validated (csrc/variates.cuh). */
+int dtree_debug_gamma_ex(double alpha, int log_space, uint64_t seed, uint32_t n, float *out, int device, int exact_only);
+int dtree_debug_binomial_ex(uint32_t n_trials, double p, uint64_t seed, uint32_t n, uint32_t *out, int device,
+                            int exact_only);
+/* BINV (the sampler for n_trials * p < 30) on EVERY one of its 2^23 possible uniforms: counts[k] = how many of them
+ * give k (k <= 192). Divided by 2^23 this is the sampler's exact output law, to compare with the binomial pmf. */
+int dtree_debug_binv_law(uint32_t n_trials, double p, uint32_t counts[256], int device);
 
 /* Copies one array of the handle's device mirror back to the host (building the mirror first if it is
  * stale). which: 0 node_base u32[n_nodes+1], 1 node_total u32[n_nodes], 2 slot_count u32[n_slots],

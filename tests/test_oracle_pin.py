@@ -22,6 +22,10 @@ def _build(lib, case):
     return t
 
 
+def test_packaged_wakehurst_data_is_the_golden_fixture(pkg, wakehurst):
+    assert pkg.workloads.wakehurst() == wakehurst
+
+
 def test_wakehurst_golden(port, wakehurst):
     """reference tests/testthat/test-socialchoice.R:11-23"""
     names = wakehurst["candidates"]

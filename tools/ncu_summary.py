@@ -46,3 +46,14 @@ for f, l, s, n, i, ti in data:
 print("   by file: " + ", ".join("%s %.1f%%" % (k, 100.0 * v / tot) for k, v in byfile.most_common(8)))
 for f, l, s, n, i, ti in sorted(data, key=lambda x: -x[3])[:topn]:
     print("   %5.1f%%  inst %4.1f%%  thr/inst %4.1f  %s:%d  %s" % (100.0 * n / tot, 100.0 * i / toti, ti / max(i, 1), f, l, s[:90]))
+
+print("source lines by executed warp-instructions:")
+for f, l, s, n, i, ti in sorted(data, key=lambda x: -x[4])[:topn]:
+    print("   inst %4.1f%%  thr/inst %4.1f  stall %4.1f%%  %s:%d  %s" % (100.0 * i / toti, ti / max(i, 1), 100.0 * n / tot, f, l, s[:90]))
+print("warp-instructions by thread occupancy (threads per instruction, share of all warp-instructions):")
+buckets = collections.Counter()
+for f, l, s, n, i, ti in data:
+    if i:
+        buckets[min(int(ti / i) // 4 * 4, 28)] += i
+for b in sorted(buckets):
+    print("   %2d-%2d threads: %5.1f%%" % (b, b + 3 if b < 28 else 32, 100.0 * buckets[b] / toti))
