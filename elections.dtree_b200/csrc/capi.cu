@@ -153,6 +153,7 @@ struct dtree {
   uint64_t trie_ballots = 0;  // log entries already inserted into `tree`
   uint64_t n_nodes = 1;       // of the current mirror
   bool host_build = false;    // tuning "host_build": mirror = HostTree::flatten + upload (measurement aid)
+  int build_mode = 0;         // tuning "build_mode": 0 one cooperative kernel, 1 a launch per phase, 2 exact allocation
   int device;
   int sm_count = 0;
   size_t smem_optin = 0;
@@ -189,7 +190,8 @@ struct dtree {
   uint32_t urn_max = 8;
   uint32_t arena_cap = 0;        // > 0: per-warp / per-thread arenas hold at most this many items (forces the overflow paths)
   int64_t lane_max_splits = -1;  // lane_kernel hands an election to the replay after this many splits (-1 auto, 0 never)
-  uint32_t tau_quarters = 2;     // deferred_kernel's resolve threshold (deferred.cuh)
+  uint32_t tau_quarters = 3;     // deferred_kernel's resolve threshold (deferred.cuh)
+  uint32_t binv_max = 30;        // binomials with n p below this use inversion, the others BTRS
   uint64_t mem_avail = 0;        // device bytes the plans may use (free + held by this handle), as last queried
   int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
   // replicas on other devices for dtree_sample_posterior_multi (owned; same parameters, tree copied when stale)
@@ -212,6 +214,7 @@ DeviceParams device_params(const HostParams &P) {
   D.max_depth = P.max_depth;
   D.leaf_depth = P.max_depth - 1u;  // unsigned wrap when max_depth == 0, as in irv_node.cpp:136
   D.small_alpha = 0;
+  D.binv_max = 30.0f;
   for (uint32_t d = 0; d < kMaxCandidates; ++d) {
     double a = P.a0;
     if (P.vd) a *= (d < P.depth_factors.size()) ? P.depth_factors[d] : 1.0;
@@ -271,7 +274,8 @@ int ensure_mirror(dtree *t, cudaStream_t s) {
     BuildStats bs;
     bool too_big = false;
     CUDA_TRY(build_tree_on_device(t->dev, t->tree.P.nc, t->log_prefs.data(), t->log_offsets.data(),
-                                  t->log_offsets.size() - 1, s, &bs, &too_big));
+                                  t->log_offsets.size() - 1, s, &bs, &too_big, t->build_mode == 2 ? 0ull : 1ull << 30,
+                                  t->build_mode == 0));
     if (too_big) return fail(DTREE_ERR_STATE, "tree has too many outcome slots for 32-bit indices");
     t->stats[kOutH2D] += bs.h2d_bytes;
     t->stats[kOutBuildLaunches] = bs.launches;
@@ -434,6 +438,7 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
   a.T.slot_cand = t->dev.slot_cand.p;
   a.T.n_nodes = (uint32_t)t->n_nodes;
   a.urn_max = t->urn_max;
+  a.P.binv_max = (float)t->binv_max;
   a.tau_quarters = t->tau_quarters;
   a.scratch = t->d_scratch.p;
   a.scratch_stride = pl.stride;
@@ -1177,12 +1182,14 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
     }
     r->tree.P = t->tree.P;
     r->host_build = t->host_build;
+    r->build_mode = t->build_mode;
     r->mode = t->mode;
     r->urn_max = t->urn_max;
     r->block_threads = t->block_threads;
     r->blocks_per_sm = t->blocks_per_sm;
     r->arena_cap = t->arena_cap;
     r->tau_quarters = t->tau_quarters;
+    r->binv_max = t->binv_max;
     r->lane_max_splits = t->lane_max_splits;
     // The abort callback is the parent's: it is polled between waves below, on the calling thread, once for all
     // devices. A replica only needs to know that its job must be cut into waves.
@@ -1419,6 +1426,9 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   } else if (!strcmp(key, "urn_max")) {
     if (value < 0 || value > 8) return fail(DTREE_ERR_ARG, "urn_max must be in [0, 8]");
     t->urn_max = (uint32_t)value;
+  } else if (!strcmp(key, "binv_max")) {
+    if (value < 10 || value > 60) return fail(DTREE_ERR_ARG, "binv_max must be in [10, 60] (BTRS needs n p >= 10; inversion is exact to 192 successes)");
+    t->binv_max = (uint32_t)value;
   } else if (!strcmp(key, "tau_quarters")) {
     if (value < 1 || value > 3) return fail(DTREE_ERR_ARG, "tau_quarters must be 1, 2 or 3");
     t->tau_quarters = (uint32_t)value;
@@ -1429,6 +1439,10 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   } else if (!strcmp(key, "lane_max_splits")) {
     if (value < -1) return fail(DTREE_ERR_ARG, "lane_max_splits must be -1 (auto), 0 (no limit) or a positive count");
     t->lane_max_splits = value;
+  } else if (!strcmp(key, "build_mode")) {
+    if (value < 0 || value > 2) return fail(DTREE_ERR_ARG, "build_mode must be 0, 1 or 2");
+    t->build_mode = (int)value;
+    t->mirrored_version = ~0ull;
   } else if (!strcmp(key, "host_build")) {
     t->host_build = value != 0;
     t->mirrored_version = ~0ull;

@@ -42,6 +42,7 @@ struct DeviceParams {
   uint32_t leaf_depth;     // max_depth - 1 in unsigned arithmetic (irv_node.cpp:136), UINT32_MAX if max_depth == 0
   float a_prior[kMaxCandidates];  // a0 * (vd ? depthFactor[depth] : 1) per depth (irv_node.cpp:35,115)
   int small_alpha;         // any a_prior[d] < 1: Gamma variates are carried in log space
+  float binv_max;          // binomials with n p below this are drawn by inversion, the others by BTRS (>= 10)
 };
 
 // Level-ordered CSR mirror of the observed-count tree (IRVNode, tree_node.h:36-58).

@@ -300,7 +300,7 @@ __device__ void lane_split_big(const SimArgs &a, const LaneShared &sh, uint32_t 
         const float tot = __fadd_rn(sl, sr);
         const bool flip = sl > sr;
         uint32_t att = 0;
-        const uint32_t kk = binomial_small_p(n, __fdividef(flip ? sr : sl, tot), key, x.node_key, k, att);
+        const uint32_t kk = binomial_small_p(n, __fdividef(flip ? sr : sl, tot), key, x.node_key, k, att, a.P.binv_max);
         left = flip ? n - kk : kk;
         stat[kStatBinomials] += att;
       }

@@ -322,7 +322,7 @@ __device__ void split_items(const SimArgs &a, WarpTile<W> &wt, uint32_t m, int l
           const float tot = __fadd_rn(sl, sr);
           const bool flip = sl > sr;
           uint32_t att = 0;
-          const uint32_t kk = binomial_small_p(n, __fdividef(flip ? sr : sl, tot), key, wt.item[it].node_key, k, att);
+          const uint32_t kk = binomial_small_p(n, __fdividef(flip ? sr : sl, tot), key, wt.item[it].node_key, k, att, a.P.binv_max);
           left = flip ? n - kk : kk;
           stat[kStatBinomials] += att;
         }

@@ -4,6 +4,8 @@
 // places the children of a level in breadth-first order — the order HostTree::flatten produces.
 #include "tree_build.h"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 namespace dtb {
@@ -309,11 +311,274 @@ __global__ void __launch_bounds__(kScanBlock)
   }
 }
 
+
+// --- the whole build as ONE cooperative kernel --------------------------------------------------------------------
+// The level-synchronous build above needs ~4 launches per tree level (39 for the 10-candidate benchmark tree), each a
+// few microseconds of work: the rebuild was launch-latency-bound. Here the same phases run inside one persistent
+// grid with grid-wide barriers between them (the level table lives in device memory already, so no phase ever needed
+// the host). Used whenever the arrays sized by a priori bounds fit the budget; the multi-launch path remains for
+// trees whose bounds do not (the host then reads every level's size to allocate exactly).
+namespace cg = cooperative_groups;
+
+struct CoopArgs {
+  TreePtrs T;
+  const uint8_t *prefs;
+  const uint64_t *off;
+  uint8_t *slots;
+  uint32_t *cursor, *block_sums, *tab, *obs_tally0;
+  ObsOut O;
+  uint64_t first_new, n_ballots;
+  uint32_t nc;
+  int W;
+};
+
+template <typename F>
+__device__ __forceinline__ void tile_sum_phase(F f, uint32_t n, uint32_t *block_sums) {
+  const uint32_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  for (uint32_t vb = blockIdx.x; vb < n_tiles; vb += gridDim.x) {
+    const uint32_t first = vb * (uint32_t)kScanTile + threadIdx.x * (uint32_t)kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (first + k < n) s += f(first + k);
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[vb] = total;
+  }
+}
+
+// Exclusive scan of block_sums[0..nb) in place by the calling block; returns the total to every thread.
+__device__ __forceinline__ uint32_t scan_tiles(uint32_t *block_sums, uint32_t nb) {
+  uint32_t carry = 0;
+  for (uint32_t start = 0; start < nb; start += kScanBlock) {
+    const uint32_t i = start + threadIdx.x;
+    const uint32_t v = i < nb ? block_sums[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, &total);
+    if (i < nb) block_sums[i] = carry + ex;
+    carry += total;
+  }
+  return carry;
+}
+
+constexpr int kCountBins = 8192;  // outcome slots of a level counted in shared memory (32 KB)
+
+__global__ void __launch_bounds__(kScanBlock) build_tree_coop_kernel(const CoopArgs A) {
+  __shared__ uint32_t s_bins[kCountBins];
+  cg::grid_group grid = cg::this_grid();
+  const TreePtrs &T = A.T;
+  const uint32_t nc = A.nc, tid = threadIdx.x;
+  const uint64_t n = A.n_ballots;
+  const uint64_t gsize = (uint64_t)gridDim.x * kScanBlock, gtid = (uint64_t)blockIdx.x * kScanBlock + tid;
+  uint32_t *tab = A.tab;
+
+  // phase 0: slot sequences of the new ballots (slot_sequences_kernel) and the root (init_root_kernel)
+  for (uint64_t b = A.first_new + gtid; b < n; b += gsize) {
+    const uint64_t lo = A.off[b];
+    const uint32_t len = (uint32_t)(A.off[b + 1] - lo);
+    const uint32_t L = min(len, nc - 1u);
+    uint8_t path[kMaxCandidates];
+    for (uint32_t i = 0; i < nc; ++i) path[i] = (uint8_t)i;
+    for (uint32_t d = 0; d < L; ++d) {
+      const uint8_t c = A.prefs[lo + d];
+      uint32_t i = d;
+      while (i < nc - 1u && path[i] != c) ++i;
+      A.slots[lo + d] = (uint8_t)(i - d);
+      path[i] = path[d];
+      path[d] = c;
+    }
+    for (uint32_t d = L; d < len; ++d) A.slots[lo + d] = 0;
+  }
+  if (blockIdx.x == 0) {
+    for (uint32_t k = tid; k < (uint32_t)kTabWords; k += kScanBlock) tab[k] = 0;
+    if (tid <= nc) {
+      T.slot_count[tid] = 0;
+      T.slot_child[tid] = -1;
+      T.slot_cand[tid] = tid < nc ? (uint8_t)tid : 0xFF;
+    }
+    if (tid < (uint32_t)kMaxCandidates) A.obs_tally0[tid] = 0;
+    if (tid < (uint32_t)A.W) T.node_key[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+      T.node_base[0] = 0;
+      T.node_base[1] = nc + 1;
+      tab[1] = 1;
+      tab[4 * kTotRow + 0] = 1;
+      tab[4 * kTotRow + 1] = nc + 1;
+    }
+  }
+  grid.sync();
+
+  for (uint32_t depth = 0;; ++depth) {
+    const uint32_t K = nc - depth;
+    // count_level_kernel: one count per ballot still walking. Near the root all ballots hit a handful of slots and
+    // global atomics on them serialise (0.3 of the 0.4 ms of a 200 000-ballot rebuild), so while the level's slots
+    // fit, every block counts in shared memory and adds each touched slot once. The loop bound is block-uniform, so
+    // whole warps reach the match.
+    const uint32_t lvl_base = depth == 0 ? 0u : tab[4 * depth + 2];
+    const uint32_t lvl_slots = (depth == 0 ? 1u : tab[4 * depth + 1]) * (K + 1);
+    const bool privatise = lvl_slots <= (uint32_t)kCountBins;
+    if (privatise) {
+      for (uint32_t i = tid; i < lvl_slots; i += kScanBlock) s_bins[i] = 0;
+      __syncthreads();
+    }
+    for (uint64_t b0 = (uint64_t)blockIdx.x * kScanBlock; b0 < n; b0 += gsize) {
+      const uint64_t b = b0 + tid;
+      uint32_t idx = kDone;
+      if (b < n) {
+        const uint32_t cur = depth == 0 ? 0u : A.cursor[b];
+        if (cur != kDone) {
+          const uint32_t node = depth == 0 ? 0u : (uint32_t)T.slot_child[cur];
+          const uint32_t base = T.node_base[node];
+          const uint64_t lo = A.off[b];
+          const uint32_t len = (uint32_t)(A.off[b + 1] - lo);
+          if (len == depth) {  // irv_node.cpp:191-194
+            idx = base + K;
+            A.cursor[b] = kDone;
+          } else {
+            idx = base + A.slots[lo + depth];
+            A.cursor[b] = K == 2 ? kDone : idx;  // irv_node.cpp:210
+          }
+        } else if (depth == 0) {
+          A.cursor[b] = kDone;
+        }
+      }
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, idx);
+      if (idx != kDone && (tid & 31) == (unsigned)(__ffs(peers) - 1)) {
+        if (privatise) atomicAdd(&s_bins[idx - lvl_base], (uint32_t)__popc(peers));
+        else atomicAdd(&T.slot_count[idx], (uint32_t)__popc(peers));
+      }
+    }
+    if (privatise) {
+      __syncthreads();
+      for (uint32_t i = tid; i < lvl_slots; i += kScanBlock)
+        if (s_bins[i]) atomicAdd(&T.slot_count[lvl_base + i], s_bins[i]);
+    }
+    if (K <= 2 || n == 0) break;  // irv_node.cpp:210: a node with two candidates left has no children
+    grid.sync();
+    const uint32_t *row = tab + 4 * depth;
+    const uint32_t level_nodes = row[1];
+    if (level_nodes == 0) break;
+    const uint32_t n_items = level_nodes * (K + 1);
+    const uint32_t n_tiles = (n_items + kScanTile - 1) / kScanTile;
+    LevelFlag f{T.slot_count, row, K + 1};
+    tile_sum_phase(f, n_items, A.block_sums);
+    grid.sync();
+    if (blockIdx.x == 0) {  // scan_sums_kernel
+      const uint32_t carry = scan_tiles(A.block_sums, n_tiles);
+      if (tid == 0) {
+        uint32_t *tot = tab + 4 * kTotRow, *next = tab + 4 * (depth + 1);
+        next[0] = row[0] + row[1];
+        next[1] = carry;
+        next[2] = row[2] + row[1] * (K + 1);
+        tot[0] = next[0] + carry;
+        tot[1] = next[2] + carry * K;  // a child has one slot less than its parent
+      }
+    }
+    grid.sync();
+    {  // create_children_kernel
+      const uint32_t *next = row + 4;
+      const uint32_t level_first_node = row[0], first_new_node = next[0], n_new = next[1], new_slot_base = next[2];
+      if (blockIdx.x == 0 && tid == 0) T.node_base[first_new_node + n_new] = new_slot_base + n_new * K;
+      for (uint32_t vb = blockIdx.x; vb < n_tiles; vb += gridDim.x) {
+        const uint32_t first = vb * (uint32_t)kScanTile + tid * (uint32_t)kScanItems;
+        uint32_t flags = 0, s = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
+          if (first + k < n_items && f(first + k)) {
+            flags |= 1u << k;
+            ++s;
+          }
+        uint32_t total;
+        uint32_t rank = block_exclusive_scan(s, &total) + A.block_sums[vb];
+        for (int k = 0; k < kScanItems; ++k) {
+          if (!(flags >> k & 1u)) continue;
+          const uint32_t i = first + k, pn = i / (K + 1), j = i % (K + 1);
+          const uint32_t slot = row[2] + i, pbase = row[2] + pn * (K + 1);
+          const uint32_t child = first_new_node + rank, cbase = new_slot_base + rank * K;
+          ++rank;
+          T.slot_child[slot] = (int32_t)child;
+          T.node_base[child] = cbase;
+          for (uint32_t q = 0; q + 1 < K; ++q) {
+            T.slot_cand[cbase + q] = (q + 1 == j) ? T.slot_cand[pbase] : T.slot_cand[pbase + q + 1];
+            T.slot_child[cbase + q] = -1;
+            T.slot_count[cbase + q] = 0;
+          }
+          T.slot_cand[cbase + K - 1] = 0xFF;
+          T.slot_child[cbase + K - 1] = -1;
+          T.slot_count[cbase + K - 1] = 0;
+          const uint32_t parent = level_first_node + pn;
+          const uint64_t cand = T.slot_cand[slot];
+          for (int w = 0; w < A.W; ++w) {
+            uint64_t key = T.node_key[(size_t)parent * A.W + w];
+            if ((int)(depth / kPrefsPerWord) == w) key |= cand << (kPrefBits * (depth % kPrefsPerWord));
+            T.node_key[(size_t)child * A.W + w] = key;
+          }
+        }
+      }
+    }
+    grid.sync();
+  }
+  grid.sync();
+  // node totals and the packed observed multiset (node_totals_kernel, tile/scan, write_observed_kernel)
+  const uint32_t n_nodes = tab[4 * kTotRow];
+  for (uint64_t i = gtid; i < n_nodes; i += gsize) {
+    const uint32_t base = T.node_base[i], K = T.node_base[i + 1] - base - 1u;
+    uint32_t s = 0;
+    for (uint32_t j = 0; j < K; ++j) s += T.slot_count[base + j];
+    T.node_total[i] = s;
+  }
+  ObservedFlag of{T.node_base, T.slot_count};
+  tile_sum_phase(of, n_nodes, A.block_sums);
+  grid.sync();
+  const uint32_t node_tiles = (n_nodes + kScanTile - 1) / kScanTile;
+  if (blockIdx.x == 0) {
+    const uint32_t carry = scan_tiles(A.block_sums, node_tiles);
+    if (tid == 0) tab[4 * kTotRow + 2] = carry;
+  }
+  grid.sync();
+  for (uint32_t vb = blockIdx.x; vb < node_tiles; vb += gridDim.x) {
+    const uint32_t first = vb * (uint32_t)kScanTile + tid * (uint32_t)kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (first + k < n_nodes) s += of(first + k);
+    uint32_t total;
+    uint32_t at = block_exclusive_scan(s, &total) + A.block_sums[vb];
+    if (s == 0) continue;
+    for (int k = 0; k < kScanItems; ++k) {
+      const uint32_t i = first + k;
+      if (i >= n_nodes) break;
+      const uint32_t base = T.node_base[i], K = T.node_base[i + 1] - base - 1u, depth = nc - K;
+      const uint32_t stop = T.slot_count[base + K];
+      if (stop) write_observed(T, A.O, at++, i, depth, -1, stop, nc, A.W);
+      if (K == 2u)
+        for (uint32_t j = 0; j < 2u; ++j) {
+          const uint32_t c = T.slot_count[base + j];
+          if (c) write_observed(T, A.O, at++, i, depth, (int)T.slot_cand[base + j], c, nc, A.W);
+        }
+    }
+  }
+}
+
 #define BUILD_TRY(expr)              \
   do {                               \
     cudaError_t e_ = (expr);         \
     if (e_ != cudaSuccess) return e_; \
   } while (0)
+
+// Co-resident blocks per SM of the cooperative build kernel (0: cooperative launch not available).
+int coop_blocks_per_sm() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, coop = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, build_tree_coop_kernel, kScanBlock, 0) != cudaSuccess)
+      n = 0;
+    cached = n;
+  }
+  return cached;
+}
 
 TreePtrs ptrs(DeviceTreeStore &S) {
   return TreePtrs{S.node_base.p, S.node_total.p, S.slot_count.p, S.slot_child.p, S.slot_cand.p, S.node_key.p};
@@ -336,7 +601,7 @@ cudaError_t grow_slots(DeviceTreeStore &S, size_t slots, size_t keep, cudaStream
 
 cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t *h_prefs, const uint64_t *h_offsets,
                                  uint64_t n_ballots, cudaStream_t stream, BuildStats *stats, bool *too_big,
-                                 uint64_t bound_budget_bytes) {
+                                 uint64_t bound_budget_bytes, bool allow_cooperative) {
   const int W = key_words_for(nc);
   BuildStats st;
   if (too_big) *too_big = false;
@@ -351,6 +616,8 @@ cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t 
 
   // 1. append the new part of the ballot log and compute its slot sequences
   if (n_ballots < S.log_ballots) S.log_ballots = S.log_bytes = 0;  // the log was reset
+  uint64_t first_new = n_ballots;  // cooperative path: the kernel computes the slot sequences of [first_new, n_ballots)
+  bool slots_pending = false;
   if (n_ballots > S.log_ballots) {
     const uint64_t old_b = S.log_ballots, old_bytes = S.log_bytes, bytes = h_offsets[n_ballots];
     BUILD_TRY(S.log_prefs.grow(bytes, old_bytes, stream));
@@ -361,10 +628,8 @@ cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t 
     BUILD_TRY(cudaMemcpyAsync(S.log_off.p + old_b, h_offsets + old_b, (n_ballots - old_b + 1) * sizeof(uint64_t),
                               cudaMemcpyHostToDevice, stream));
     st.h2d_bytes += (bytes - old_bytes) + (n_ballots - old_b + 1) * sizeof(uint64_t);
-    const uint64_t fresh = n_ballots - old_b;
-    const int grid = (int)std::min<uint64_t>((fresh + 127) / 128, 1u << 16);
-    slot_sequences_kernel<<<grid, 128, 0, stream>>>(S.log_prefs.p, S.log_off.p, S.log_slots.p, old_b, n_ballots, nc);
-    ++st.launches;
+    first_new = old_b;
+    slots_pending = true;
     S.log_ballots = n_ballots;
     S.log_bytes = bytes;
   }
@@ -381,7 +646,60 @@ cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t 
   const uint64_t ub_bytes = ub_total * (8 + 8ull * W) + ub_slots * 9 + n_ballots * (8ull * W + 5);
   const bool bounded = ub_bytes <= bound_budget_bytes && ub_slots < 0xFFFFFFF0ull;
 
-  // 3. root
+  // 3. the whole build in one cooperative launch when the bounds fit (no host round trip until the end)
+  if (bounded && allow_cooperative && coop_blocks_per_sm() > 0) {
+    BUILD_TRY(grow_nodes(S, ub_total, 0, W, stream));
+    BUILD_TRY(grow_slots(S, ub_slots, 0, stream));
+    BUILD_TRY(S.node_total.grow(ub_total, 0, stream));
+    BUILD_TRY(S.obs_tally0.reserve(kMaxCandidates));
+    BUILD_TRY(S.cursor.grow(std::max<uint64_t>(n_ballots, 1), 0, stream));
+    uint64_t max_items = std::max<uint64_t>(ub_total, 1);
+    for (uint32_t d = 0; nc - d > 2; ++d) max_items = std::max<uint64_t>(max_items, ub_nodes[d] * (nc - d + 1));
+    BUILD_TRY(S.block_sums.grow((max_items + kScanTile - 1) / kScanTile + 1, 0, stream));
+    const uint64_t obs_cap = std::max<uint64_t>(n_ballots, 1);  // every entry stands for at least one ballot
+    BUILD_TRY(S.obs_key.grow((size_t)obs_cap * W, 0, stream));
+    BUILD_TRY(S.obs_cnt.grow(obs_cap, 0, stream));
+    BUILD_TRY(S.obs_first.grow(obs_cap, 0, stream));
+    CoopArgs A;
+    A.T = ptrs(S);
+    A.prefs = S.log_prefs.p;
+    A.off = S.log_off.p;
+    A.slots = S.log_slots.p;
+    A.cursor = S.cursor.p;
+    A.block_sums = S.block_sums.p;
+    A.tab = tab;
+    A.obs_tally0 = S.obs_tally0.p;
+    A.O = ObsOut{S.obs_key.p, S.obs_cnt.p, S.obs_tally0.p, S.obs_first.p};
+    A.first_new = first_new;
+    A.n_ballots = n_ballots;
+    A.nc = nc;
+    A.W = W;
+    int dev = 0, sms = 0;
+    BUILD_TRY(cudaGetDevice(&dev));
+    BUILD_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // One block per SM at most: a grid-wide barrier costs more the more blocks take part, and the phases are short
+    // chains of dependent loads rather than bandwidth (measured on the 200 000-ballot benchmark tree: 0.40 ms with
+    // 148 blocks, 0.44 with 296, 0.49 with 592; 0.41 as 38 separate launches).
+    const uint64_t want = std::max<uint64_t>(1, (std::max<uint64_t>(n_ballots, max_items / 4) + 2 * kScanBlock - 1) / (2 * kScanBlock));
+    const int grid = (int)std::min<uint64_t>(want, (uint64_t)std::min(coop_blocks_per_sm(), 1) * sms);
+    void *args[] = {&A};
+    BUILD_TRY(cudaLaunchCooperativeKernel((const void *)build_tree_coop_kernel, dim3(grid), dim3(kScanBlock), args, 0, stream));
+    ++st.launches;
+    BUILD_TRY(read_table());
+    S.n_nodes = S.h_tab[4 * kTotRow];
+    S.n_slots = S.h_tab[4 * kTotRow + 1];
+    S.n_obs = S.h_tab[4 * kTotRow + 2];
+    if (stats) *stats = st;
+    return cudaSuccess;
+  }
+  if (slots_pending) {
+    const uint64_t fresh = n_ballots - first_new;
+    const int grid = (int)std::min<uint64_t>((fresh + 127) / 128, 1u << 16);
+    slot_sequences_kernel<<<grid, 128, 0, stream>>>(S.log_prefs.p, S.log_off.p, S.log_slots.p, first_new, n_ballots, nc);
+    ++st.launches;
+  }
+
+  // 3b. root (multi-launch path)
   if (bounded) {
     BUILD_TRY(grow_nodes(S, ub_total, 0, W, stream));
     BUILD_TRY(grow_slots(S, ub_slots, 0, stream));

@@ -41,10 +41,12 @@ struct BuildStats {
 // Appends ballots [S.log_ballots, n_ballots) of the host log (prefs/offsets as given to dtree_update,
 // already validated) to the device log and rebuilds the mirror. Returns a CUDA error; `too_big` is set
 // when the tree needs more than 2^32-16 slots. When the arrays sized by a priori bounds (a level has at most
-// min(#ballots, parents x children) nodes) fit `bound_budget_bytes`, the whole build is enqueued without a host
-// round trip and synchronised once; otherwise the host reads every level's size to allocate exactly.
+// min(#ballots, parents x children) nodes) fit `bound_budget_bytes`, the whole build is ONE cooperative kernel
+// (grid-wide barriers between the phases of every level) or, with allow_cooperative = false, the same phases as ~4
+// launches per level enqueued without a host round trip; otherwise the host reads every level's size to allocate
+// exactly.
 cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t *h_prefs, const uint64_t *h_offsets,
                                  uint64_t n_ballots, cudaStream_t stream, BuildStats *stats, bool *too_big,
-                                 uint64_t bound_budget_bytes = 1ull << 30);
+                                 uint64_t bound_budget_bytes = 1ull << 30, bool allow_cooperative = true);
 
 }  // namespace dtb

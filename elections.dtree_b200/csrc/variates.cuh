@@ -372,10 +372,10 @@ static __device__ __noinline__ uint32_t binomial_btrs64(uint32_t n, float ps, Rn
 // EXACT_ONLY (test hook): every acceptance test that is not a quick accept is made by the f64 function.
 template <bool EXACT_ONLY = false>
 __device__ __forceinline__ uint32_t binomial_small_p(uint32_t n, float ps, RngKey key, uint64_t node_key,
-                                                     uint32_t slot, uint32_t &attempts) {
+                                                     uint32_t slot, uint32_t &attempts, float binv_max = 30.0f) {
   if (n == 0u || !(ps > 0.0f)) return 0u;
   const float nf = (float)n;
-  if (__fmul_rn(nf, ps) < 30.0f) {
+  if (__fmul_rn(nf, ps) < binv_max) {
     const U4 r = node_random(key, node_key, kStreamBinomial + slot, 0u);
     ++attempts;
     return binv(n, ps, r.x);

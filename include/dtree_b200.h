@@ -188,6 +188,11 @@ int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user
  *        Polya-urn shortcut instead of Gamma variates, <= 8);
  *      "host_build" (0 default; 1 = build the tree with the host trie and upload it, the pre-device-build
  *        path, kept to measure against; the two mirrors are identical array for array);
+ *      "build_mode" (0 default: the device tree build is one cooperative kernel; 1: one launch per phase and level;
+ *        2: as 1 with every level's size read back by the host to allocate exactly, the path taken on its own by trees
+ *        whose a priori bounds exceed 1 GB; all three produce the same arrays);
+ *      "tau_quarters" (1..3, default 3: share of the missing margin mode 1 lets wait when it picks the nodes to split);
+ *      "binv_max" (10..60, default 30: binomials with n p below it are drawn by inversion, the others by BTRS);
  *      "arena_cap" (0 default; > 0 = modes 1 and 2 give every election a scratch arena of at most that many node
  *        records, far too small on purpose, so that tests reach the overflow paths: re-run in a shared worst-case
  *        arena (mode 1) and hand-over to the replay launch (mode 2); results do not change);

@@ -97,7 +97,14 @@ def test_device_built_tree_equals_reference_tree(pkg, L, port, nc, n, seed):
     assert int(img["obs_cnt"].sum()) == n
     firsts = np.bincount([b[0] for b in ballots if b], minlength=32)
     assert np.array_equal(img["obs_tally0"], firsts)
-    assert dev.last_stats()["build_launches"] > 0
+    assert dev.last_stats()["build_launches"] == 1  # the whole build is one cooperative kernel
+    # the same tree through the other two device build paths: a launch per phase, and exact allocation with the
+    # host reading every level's size (what trees too large for a-priori-bound allocation take on their own)
+    for mode, least in ((1, 4), (2, 4)):
+        dev.tune(build_mode=mode)
+        assert_same_image(img, dev.device_image())
+        assert dev.last_stats()["build_launches"] >= least
+    dev.tune(build_mode=0)
     o.close()
 
 

@@ -22,7 +22,7 @@ for inval in (1, 0):
                 N.check(L.dtree_invalidate_device(t._h))
             t.sample_posterior_counts(100000, cfg["n_ballots"], seed="P", first_election=i * 100000)
             st = t.last_stats()
-            for k in ("mirror_us", "plan_us", "launch_us", "finish_us", "dbg20", "dbg21", "dbg22", "dbg23"):
+            for k in ("mirror_us", "plan_us", "launch_us", "finish_us"):
                 acc[k] = acc.get(k, 0) + st[k]
         dt = (time.perf_counter() - t0) / n * 1e3
         print("invalidate=%d rep %d: %.3f ms/call" % (inval, rep, dt), {k: round(v / n, 1) for k, v in acc.items()}, flush=True)
