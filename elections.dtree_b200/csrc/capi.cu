@@ -658,11 +658,12 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
       z.lpool = z.pool; z.lqueue = z.queue; z.lbig = z.big + z.queue;
       z.nodes_per_election = (double)H.stats[kStatItems] / std::max<uint32_t>(pilot_done, 1);
     }
-    // Capacities get a 4x margin over the largest election seen and are only revised when an election has
-    // used more than half of them (so that a new maximum does not reallocate the scratch every time).
-    if (!hit || 2ull * z.pool > z.cap_pool) z.cap_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 4ull * z.pool + 4096);
-    if (!hit || 2ull * z.queue > z.cap_queue) z.cap_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 4ull * z.queue + 4096);
-    if (!hit || 2ull * z.big > z.cap_big) z.cap_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 4ull * z.big + 1024);
+    // Capacities get a 2x margin (+ a constant that matters for light elections only) over the largest election seen
+    // and are only revised when an election has used more than 70 % of them, so that a new maximum does not
+    // reallocate the scratch every time. An election that still outgrows its arena re-runs in a worst-case one.
+    if (!hit || 10ull * z.pool > 7ull * z.cap_pool) z.cap_pool = (uint32_t)std::min<uint64_t>(pl.arena_items, 2ull * z.pool + 2048);
+    if (!hit || 10ull * z.queue > 7ull * z.cap_queue) z.cap_queue = (uint32_t)std::min<uint64_t>(pl.arena_queue, 2ull * z.queue + 2048);
+    if (!hit || 10ull * z.big > 7ull * z.cap_big) z.cap_big = (uint32_t)std::min<uint64_t>(pl.arena_big, 2ull * z.big + 512);
     pl.cap_items = std::min(z.cap_pool, pl.arena_items);
     pl.cap_queue = std::min(z.cap_queue, pl.arena_queue);
     pl.cap_big = std::min(z.cap_big, pl.arena_big);

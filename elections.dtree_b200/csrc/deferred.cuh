@@ -28,6 +28,10 @@
 
 #include "split.cuh"
 
+#ifndef DTB_DEFERRED_THREADS_PER_SM
+#define DTB_DEFERRED_THREADS_PER_SM 512  // resident threads per SM the register allocation aims at (128 registers each)
+#endif
+
 namespace dtb {
 
 typedef Item<1> DItem;  // prefix unused; pad_ = depth
@@ -43,6 +47,7 @@ struct DeferredWarp {
   uint32_t n_pool;    // high-water mark of the parked-node pool
   int32_t n_free;     // free-list depth (may dip below 0 while lanes race for the last free slots)
   uint32_t q_tail;    // small-count work queue (circular, monotone counters; q_head is a register)
+  uint32_t q1_head, q1_tail;  // the same for the queue of single-ballot nodes
   uint32_t big_tail;  // big-count list of waiting nodes (big[0])
   uint32_t overflow;
   uint32_t unresolved;      // ballots (sampled + observed) inside the waiting nodes
@@ -69,11 +74,13 @@ struct DeferredScratch {
   DItem *pool;
   uint8_t *holder;
   uint32_t *free_list;
-  DItem *queue;
+  DItem *queue;   // small sampled counts, more than one ballot inside
+  DItem *queue1;  // nodes holding exactly one ballot: the bulk of what waits deep in a large tree, and wanted only
+                  // when a round cannot be settled otherwise, so they are kept out of the other passes' way
   DItem *big[2];
   __host__ __device__ static uint64_t a16(uint64_t x) { return (x + 15) & ~15ull; }
   __host__ __device__ static uint64_t bytes(uint32_t cap, uint32_t capq, uint32_t capb) {
-    return (uint64_t)cap * sizeof(DItem) + a16(cap) + a16((uint64_t)cap * 4) + (uint64_t)capq * sizeof(DItem) +
+    return (uint64_t)cap * sizeof(DItem) + a16(cap) + a16((uint64_t)cap * 4) + 2 * (uint64_t)capq * sizeof(DItem) +
            2 * (uint64_t)capb * sizeof(DItem);
   }
   __device__ void bind(uint8_t *p, uint32_t cap, uint32_t capq, uint32_t capb) {
@@ -81,6 +88,7 @@ struct DeferredScratch {
     holder = p; p += a16(cap);
     free_list = (uint32_t *)p; p += a16((uint64_t)cap * 4);
     queue = (DItem *)p; p += (uint64_t)capq * sizeof(DItem);
+    queue1 = (DItem *)p; p += (uint64_t)capq * sizeof(DItem);
     big[0] = (DItem *)p; p += (uint64_t)capb * sizeof(DItem);
     big[1] = (DItem *)p;
   }
@@ -96,6 +104,10 @@ __device__ __forceinline__ void enqueue_node(const SimArgs &a, DeferredWarp &ws,
     atomicAdd(&ws.big_cnt[mass_class(m)], 1u);
     const uint32_t q = coalesced_reserve(&ws.big_tail);
     if (q < cp.big) sc.big[0][q] = ch;
+    else ws.overflow = 1;
+  } else if (m == 1u) {
+    const uint32_t q = coalesced_reserve(&ws.q1_tail);
+    if (q - ws.q1_head < cp.queue) sc.queue1[q % cp.queue] = ch;
     else ws.overflow = 1;
   } else {
     atomicMax(&ws.small_mass_max, m);
@@ -248,9 +260,32 @@ __device__ void split_big_nodes(const SimArgs &a, WarpTile<1> &wt, DeferredWarp 
 // is out join the waiting lists (and wait for the next call).
 template <bool LOG>
 __device__ void deferred_resolve(const SimArgs &a, WarpTile<1> &wt, DeferredWarp &ws, const DeferredScratch &sc,
-                                 const DeferredCaps &cp, uint32_t &q_head, uint32_t &hw_queue, uint32_t &hw_big,
-                                 uint32_t eliminated, uint32_t tau, int log_dp_max, const RngKey key, uint32_t *stat) {
+                                 const DeferredCaps &cp, uint32_t &q_head, uint32_t &q1_head, uint32_t &hw_queue,
+                                 uint32_t &hw_big, uint32_t eliminated, uint32_t tau, int log_dp_max, const RngKey key,
+                                 uint32_t *stat) {
   const int lane = threadIdx.x & 31;
+  __syncwarp();
+  // single-ballot nodes: only when every waiting ballot counts (tau == 1); all of them are split, none goes back
+  const uint32_t n_one = ws.q1_tail - q1_head;
+  hw_queue = max(hw_queue, n_one);
+  if (n_one && tau <= 1u) {
+    for (uint32_t done = 0; done < n_one && !ws.overflow; done += 32u) {
+      const uint32_t m = min(32u, n_one - done);
+      DItem x;
+      if ((uint32_t)lane < m) x = sc.queue1[(q1_head + lane) % cp.queue];
+      q1_head += m;
+      __syncwarp();  // the batch has been read: its queue slots may be reused from here on
+      if (lane == 0) ws.q1_head = q1_head;
+      __syncwarp();
+      if ((uint32_t)lane < m) {
+        stat[kStatRereads] += 1;
+        atomicSub(&ws.unresolved, 1u);
+        atomicSub(&ws.hist[0], 1u);
+        split_small_node(a, ws, sc, cp, x, eliminated, key, stat);
+      }
+      __syncwarp();
+    }
+  }
   __syncwarp();
   // small counts: one turn of the circular queue, 32 nodes at a time, one lane each
   const uint32_t n_small = ws.q_tail - q_head;
@@ -362,6 +397,8 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
     ws.overflow = 0;
     ws.q_tail = 0;
     ws.q_head = 0;
+    ws.q1_tail = 0;
+    ws.q1_head = 0;
     ws.big_tail = 0;
     ws.unresolved = (uint32_t)root.prefix.w[0];
     ws.small_mass_max = 0;
@@ -371,14 +408,14 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
       sc.big[0][0] = root;
       ws.big_tail = 1;
       ws.big_cnt[mass_class((uint32_t)root.prefix.w[0])] = 1;
-    } else {
+    } else {  // (the queue of nodes with a small count; its mass is "positive", not a ballot count, at the root)
       sc.queue[0] = root;
       ws.q_tail = 1;
       ws.small_mass_max = (uint32_t)root.prefix.w[0];
     }
   }
   __syncwarp();
-  uint32_t eliminated = 0, tie_rounds = 0, my_order = 0xFFu, q_head = 0, hw_queue = 0, hw_big = 0;
+  uint32_t eliminated = 0, tie_rounds = 0, my_order = 0xFFu, q_head = 0, q1_head = 0, hw_queue = 0, hw_big = 0;
   const bool early_stop = a.n_winners == 1u && a.elim_orders == nullptr;
 
   for (uint32_t round = 0; round < n_rounds && !ws.overflow; ++round) {
@@ -425,7 +462,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
       const uint32_t fits = __ballot_sync(0xffffffffu, lane == 0 || lighter <= allow);
       const uint32_t cls = 31u - (uint32_t)__clz(fits);  // bit 0 is always set
       const uint32_t tau = cls == 0u ? 1u : (1u << cls);
-      deferred_resolve<LOG>(a, wt, ws, sc, cp, q_head, hw_queue, hw_big, eliminated, tau, log_dp_max, key, stat);
+      deferred_resolve<LOG>(a, wt, ws, sc, cp, q_head, q1_head, hw_queue, hw_big, eliminated, tau, log_dp_max, key, stat);
     }
     if (won || ws.overflow) break;
     if (ntied > 1u) {  // uniform among the tied, ascending index (irv_ballot.cpp:100-102)
@@ -478,7 +515,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
   __syncwarp();
   if (lane == 0) stat[kStatEntries] += ws.rec_w;
   usage[0] = max(usage[0], min(ws.n_pool, 0x7FFFFFFFu));
-  usage[1] = max(usage[1], max(hw_queue, ws.q_tail - q_head));
+  usage[1] = max(usage[1], max(hw_queue, max(ws.q_tail - q_head, ws.q1_tail - q1_head)));
   usage[2] = max(usage[2], max(hw_big, min(ws.big_tail, cp.big)));
   eliminated_out = eliminated;
   order_out = my_order;
@@ -487,7 +524,7 @@ __device__ bool deferred_election(const SimArgs &a, WarpTile<1> &wt, DeferredWar
 }
 
 template <int BLOCK, bool LOG>
-__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) deferred_kernel(const __grid_constant__ SimArgs a) {
+__global__ void __launch_bounds__(BLOCK, DTB_DEFERRED_THREADS_PER_SM / BLOCK) deferred_kernel(const __grid_constant__ SimArgs a) {
   __shared__ WarpTile<1> tiles[BLOCK / 32];
   __shared__ DeferredWarp wstate[BLOCK / 32];
   __shared__ uint32_t s_wins[kMaxCandidates];
