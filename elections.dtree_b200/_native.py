@@ -46,6 +46,8 @@ _SIGS = {
     "dtree_observed": (C.c_int, [vp, C.POINTER(vp)]),
     "dtree_sample_posterior": (C.c_int, [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p,
                                          C.c_size_t, u64p, u8p]),
+    "dtree_sample_posterior_sc": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p,
+                                            C.c_size_t, u64p]),
     "dtree_sample_posterior_device": (C.c_int, [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                                 C.c_char_p, C.c_size_t, vp, vp]),
     "dtree_sample_posterior_multi": (C.c_int, [vp, C.POINTER(C.c_int), C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,

@@ -251,7 +251,7 @@ class dirichlet_tree:
         return {c: counts[i] / float(n_elections) for i, c in enumerate(self._candidates)}
 
     def sample_posterior_counts(self, n_elections, n_ballots, n_winners=1, replace=False, n_threads=None, seed=None,
-                                first_election=0, return_orders=False, devices=None):
+                                first_election=0, return_orders=False, devices=None, sc_function="irv"):
         if n_elections <= 0:
             raise ValueError("`n_elections` must be an integer > 0.")
         if n_elections > 0xFFFFFFFF or n_ballots > 0xFFFFFFFF:  # unsigned in the reference too (R_tree.h:86-88)
@@ -264,6 +264,16 @@ class dirichlet_tree:
         seed = (gseed() if seed is None else seed).encode()
         nc = self.n_candidates
         wins = np.zeros(nc, dtype=np.uint64)
+        if sc_function != "irv":  # R/social_choice.R:35-97 on every simulated election
+            if sc_function == "stv":
+                raise NotImplementedError("'stv' social choice not implemented.")  # social_choice.R:94-96
+            if sc_function != "plurality":
+                raise ValueError("`sc_function` must be one of 'plurality', 'irv' or 'stv'.")
+            if return_orders or devices is not None or n_winners != 1:
+                raise ValueError("plurality: single device, n_winners = 1, no elimination orders")
+            N.check(self._L.dtree_sample_posterior_sc(self._h, 1, int(first_election), int(n_elections), int(n_ballots),
+                                                      int(replace), seed, len(seed), wins.ctypes.data_as(N.u64p)))
+            return wins
         if devices is not None:  # one process, several GPUs (dtree_sample_posterior_multi)
             if return_orders:
                 raise ValueError("elimination orders are only returned by single-device calls")

@@ -540,11 +540,12 @@ struct Job {
   uint32_t nc = 0;
   uint64_t first_election = 0, n_elections = 0, done = 0, pilot_done = 0, wave = 0, launches = 0;
   bool want_orders = false;
+  bool replay_launch = true;  // lane mode: a deferred_kernel launch behind every wave replays what lane_kernel handed over
 };
 
 int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots, uint32_t n_winners,
                 int replace, const char *seed, size_t seed_len, unsigned long long *d_wins, bool want_orders,
-                cudaStream_t s) {
+                cudaStream_t s, int sc_function = DTREE_SC_IRV) {
   j.t = t;
   j.s = s;
   j.first_election = first_election;
@@ -556,6 +557,10 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
   if ((uint64_t)n_ballots < t->n_observed)  // R_tree.cpp:183-186
     return fail(DTREE_ERR_STATE, "`nBallots` must be larger than the number of ballots observed to obtain the posterior.");
   if (n_winners < 1 || n_winners >= nc) return fail(DTREE_ERR_ARG, "n_winners must be in [1, n_candidates)");
+  if (sc_function != DTREE_SC_IRV && sc_function != DTREE_SC_PLURALITY)
+    return fail(DTREE_ERR_ARG, "sc_function must be DTREE_SC_IRV or DTREE_SC_PLURALITY (stv is not implemented, as in R/social_choice.R:94-96)");
+  if (sc_function == DTREE_SC_PLURALITY && (n_winners != 1 || want_orders))
+    return fail(DTREE_ERR_ARG, "plurality reports the candidate(s) with the most first preferences: n_winners must be 1 and there is no elimination order");
   if (n_elections == 0) return DTREE_OK;
   {
     NvtxRange nv("dtree:mirror");
@@ -570,6 +575,52 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
   const uint32_t n_sample = replace ? n_ballots : n_ballots - (uint32_t)t->n_observed;
   Plan &pl = j.pl, &pp = j.pp;
   pl = Plan();
+  if (sc_function == DTREE_SC_PLURALITY) {
+    // Only the root is split: a thread per election (lane_kernel) in a token arena — at most n_candidates children
+    // are parked and nothing ever waits, so no pilot, no replay.
+    rc = ensure_result_block(t);
+    if (rc) return rc;
+    ResultBlock *R = t->d_res.p;
+    CUDA_TRY(cudaMemsetAsync(&R->stats[0], 0, sizeof(ResultBlock) - offsetof(ResultBlock, stats), s));
+    const HostParams &P = t->tree.P;
+    pl.W = 1;
+    pl.log_gamma = device_params(P).small_alpha != 0;
+    pl.deferred = pl.lane = true;
+    pl.block = 128;
+    pl.cap_items = 64;
+    pl.cap_queue = 8;
+    pl.cap_big = 16;
+    pl.stride = (lane_scratch_bytes(pl.cap_items, pl.cap_queue, pl.cap_big) + 255) & ~255ull;
+    pl.stride_block = pl.stride * pl.block;
+    int occ = lane_blocks_per_sm(device_params(P), pl.log_gamma);
+    if (occ <= 0) return fail(DTREE_ERR_CUDA, "lane kernel cannot be resident");
+    const uint64_t need = ((uint64_t)n_elections + pl.block - 1) / pl.block;
+    pl.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)occ * t->sm_count, need));
+    CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));
+    CUDA_TRY(t->d_retry.reserve(8));
+    SimArgs &a = j.a;
+    fill_args(t, pl, a);
+    a.n_obs = 0;
+    a.use_obs = use_obs ? 1 : 0;
+    a.seed = hash_seed(seed, seed_len);
+    a.n_sample = n_sample;
+    a.n_winners = 1;
+    a.run_irv = 1;
+    a.sc_function = DTREE_SC_PLURALITY;
+    a.win_counts = d_wins;
+    a.retry_list = t->d_retry.p + 4;
+    a.retry_count = t->d_retry.p;
+    a.retry_cap = 0;
+    a.usage = nullptr;
+    j.replay_launch = false;
+    j.wave = std::max<uint64_t>(1, n_elections);
+    j.done = j.pilot_done = 0;
+    t->stats[kOutElections] = n_elections;
+    t->stats[kOutScratchBytes] = pl.stride_block * pl.grid;
+    t->stats[kOutMode] = 2;
+    t->stats[kOutPlanUs] += tm_plan.us();
+    return DTREE_OK;
+  }
   pl.deferred = t->mode == 1 || t->mode == 2;
   bool want_lane = t->mode == 2;
   if (t->mode < 0) pl.deferred = true;  // the deferred kernels are the faster ones on every configuration measured
@@ -785,7 +836,7 @@ int job_launch_wave(Job &j) {
   if (j.pl.lane) CUDA_TRY(cudaMemsetAsync(t->d_retry.p, 0, sizeof(unsigned int), j.s));
   CUDA_TRY(launch(j.pl, a, j.s));
   ++j.launches;
-  if (j.pl.lane) {
+  if (j.pl.lane && j.replay_launch) {
     NvtxRange nv2("dtree:replay");
     SimArgs &ar = j.ar;
     ar.work_counter = &R->counter;
@@ -810,10 +861,10 @@ int job_launch_wave(Job &j) {
 // Common body of the sample_posterior entry points. d_wins must be device memory on t->device.
 int run_posterior(dtree *t, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots, uint32_t n_winners,
                   int replace, const char *seed, size_t seed_len, unsigned long long *d_wins, uint8_t *h_orders,
-                  cudaStream_t s, bool sync_at_end) {
+                  cudaStream_t s, bool sync_at_end, int sc_function = DTREE_SC_IRV) {
   Job j;
   int rc = job_prepare(j, t, first_election, n_elections, n_ballots, n_winners, replace, seed, seed_len, d_wins,
-                       h_orders != nullptr, s);
+                       h_orders != nullptr, s, sc_function);
   if (rc || n_elections == 0) return rc;
   while (j.done < j.n_elections) {
     if (t->should_abort && j.done > j.pilot_done) {
@@ -1123,6 +1174,29 @@ int dtree_sample_posterior(dtree_t *t, uint64_t first_election, uint32_t n_elect
                      elim_orders, 0, true);
   if (rc || n_elections == 0) return rc;
   for (uint32_t c = 0; c < nc; ++c) win_counts[c] = t->h_res->wins[c];  // came back with the result block
+  return DTREE_OK;
+}
+
+int dtree_sample_posterior_sc(dtree_t *t, int sc_function, uint64_t first_election, uint32_t n_elections, uint32_t n_ballots,
+                              int replace, const char *seed, size_t seed_len, uint64_t *win_counts) {
+  if (!t || !win_counts) return fail(DTREE_ERR_ARG, "null argument");
+  if (sc_function == DTREE_SC_IRV)
+    return dtree_sample_posterior(t, first_election, n_elections, n_ballots, 1, replace, seed, seed_len, win_counts, nullptr);
+  NvtxRange nv("dtree_sample_posterior_sc");
+  int rc = bind_device(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  if (!g.ok) return fail(DTREE_ERR_CUDA, "cannot select device %d", t->device);
+  const uint32_t nc = t->tree.P.nc;
+  begin_call_stats(t);
+  rc = ensure_result_block(t);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(t->d_res.p->wins, 0, sizeof t->d_res.p->wins, 0));
+  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = 0;
+  rc = run_posterior(t, first_election, n_elections, n_ballots, 1, replace, seed, seed_len, t->d_res.p->wins, nullptr, 0,
+                     true, sc_function);
+  if (rc || n_elections == 0) return rc;
+  for (uint32_t c = 0; c < nc; ++c) win_counts[c] = t->h_res->wins[c];
   return DTREE_OK;
 }
 

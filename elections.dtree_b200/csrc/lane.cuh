@@ -387,6 +387,21 @@ __global__ void __launch_bounds__(BLOCK, 768 / BLOCK) lane_kernel(const __grid_c
       root.pad_ = 0;
       split_node(active, root);  // the root holds every ballot: split at once
     }
+    if (a.sc_function == 1) {
+      // Plurality (R/social_choice.R:58-83): the candidates with the most first preferences, all of them when tied.
+      // First preferences are the root's split plus the observed first preferences that rode along: nothing below
+      // the root is ever drawn.
+      if (active) {
+        uint32_t best = 0;
+#pragma unroll 1
+        for (uint32_t c = 0; c < nc; ++c) best = max(best, sh.tally[c * 32u + lane]);
+#pragma unroll 1
+        for (uint32_t c = 0; c < nc; ++c)
+          if (best != 0u && sh.tally[c * 32u + lane] == best) atomicAdd(&s_wins[c], 1u);
+      }
+      __syncwarp();
+      continue;
+    }
     for (uint32_t round = 0; round < n_rounds; ++round) {
       bool pending = !decided && !st.overflow;  // this lane still has to settle the round
       for (;;) {

@@ -45,6 +45,7 @@ struct SimArgs {
   uint32_t n_winners;
   uint32_t urn_max;
   int run_irv;                // 0: expansion only (predictive / posterior_set dumps)
+  int sc_function;            // social choice function run on each election: 0 IRV, 1 plurality (lane_kernel only)
   int use_obs;                // observed ballots are part of the election (replace == false)
   // per-block scratch
   uint8_t *scratch;

@@ -117,6 +117,18 @@ int dtree_sample_posterior(dtree_t *t, uint64_t first_election, uint32_t n_elect
                            uint32_t n_ballots, uint32_t n_winners, int replace, const char *seed,
                            size_t seed_len, uint64_t *win_counts, uint8_t *elim_orders);
 
+/* The same posterior simulation under another social choice function (R/social_choice.R:35-97 offers "plurality",
+ * "irv" and an unimplemented "stv"; the reference's sample_posterior is IRV only, R_tree.cpp:226-227):
+ *   DTREE_SC_IRV        what dtree_sample_posterior does with n_winners = 1;
+ *   DTREE_SC_PLURALITY  R/social_choice.R:58-83 on every simulated election: first preferences only, blank ballots
+ *                       dropped, win_counts[c] += 1 for EVERY candidate with the maximal tally (ties give several
+ *                       winners, as `which(frequencies == max(frequencies))` does; an election without a single first
+ *                       preference has none). Only the root of the tree is ever sampled. */
+#define DTREE_SC_IRV 0
+#define DTREE_SC_PLURALITY 1
+int dtree_sample_posterior_sc(dtree_t *t, int sc_function, uint64_t first_election, uint32_t n_elections,
+                              uint32_t n_ballots, int replace, const char *seed, size_t seed_len, uint64_t *win_counts);
+
 /* Same, for callers that keep the result on the device (one rank per GPU reducing with NCCL):
  * d_win_counts is DEVICE memory [n_candidates] uint64 on the handle's device and is ADDED to;
  * work is enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and the call
