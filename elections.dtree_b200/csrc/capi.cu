@@ -930,7 +930,24 @@ int run_dump(dtree *t, uint64_t election, uint32_t n_sample, const char *seed, s
     CUDA_TRY(cudaMemcpy(len.data(), p_len, (size_t)n, cudaMemcpyDeviceToHost));
   }
   t->stats[kOutD2H] += (uint64_t)n * (W * 8 + 5);
-  for (uint32_t i = 0; i < n; ++i) {
+  // The kernel appends entries in whatever order its warps finish, which varies from launch to launch; the list is
+  // returned in a canonical order (by ballot, lexicographic in the candidate indices, a prefix before its
+  // extensions) so that the same seed gives the same R object (tests/testthat/test-determinism.R:5-22).
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+  auto pref = [&](uint32_t i, uint32_t j) {
+    return (uint32_t)((keys[(size_t)i * W + j / kPrefsPerWord] >> (kPrefBits * (j % kPrefsPerWord))) & 31u);
+  };
+  std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+    const uint32_t m = std::min<uint32_t>(len[x], len[y]);
+    for (uint32_t j = 0; j < m; ++j) {
+      const uint32_t a = pref(x, j), b = pref(y, j);
+      if (a != b) return a < b;
+    }
+    return len[x] < len[y];
+  });
+  for (uint32_t oi = 0; oi < n; ++oi) {
+    const uint32_t i = order[oi];
     for (uint32_t j = 0; j < len[i]; ++j) {
       uint64_t w = keys[(size_t)i * W + j / kPrefsPerWord];
       out->prefs.push_back((uint8_t)((w >> (kPrefBits * (j % kPrefsPerWord))) & 31u));

@@ -245,20 +245,35 @@ def test_product_sources_never_touch_the_oracle(pkg):
                 assert "oracle" not in src.replace("checked against the CPU oracle", ""), os.path.join(dp, f)
 
 
-def test_rcpp_shim_compiles_against_the_c_abi():
-    """INTEGRATION.md's Rcpp layer (elections.dtree_b200/host/r/R_tree_b200.cpp) is syntax-checked against
-    include/dtree_b200.h with a minimal Rcpp stand-in, since R is not installed in this image."""
+def build_shim_driver(out_path):
+    """Compiles tests/shim/shim_driver.cpp — the Rcpp shim itself plus the replay of the reference's testthat
+    scenarios — against tests/stubs/Rcpp.h and links it with lib/libdtree_b200.so. Returns the g++ result."""
     import shutil
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     gxx = shutil.which("g++")
     if not gxx:
         pytest.skip("g++ not available")
-    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "tests", "stubs"),
-                        "-I" + os.path.join(root, "include"),
-                        os.path.join(root, "elections.dtree_b200", "host", "r", "R_tree_b200.cpp")],
-                       capture_output=True, text=True)
+    lib_dir = os.path.join(root, "elections.dtree_b200", "lib")
+    return subprocess.run([gxx, "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(root, "tests", "stubs"),
+                           "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "shim", "shim_driver.cpp"),
+                           "-o", out_path, "-L" + lib_dir, "-ldtree_b200", "-Wl,-rpath," + lib_dir],
+                          capture_output=True, text=True)
+
+
+def test_rcpp_shim_compiles_and_links_against_the_c_abi(tmp_path):
+    """INTEGRATION.md's Rcpp layer (elections.dtree_b200/host/r/R_tree_b200.cpp) compiles against
+    include/dtree_b200.h with the functional Rcpp stand-in of tests/stubs/ and links with the library (R is not
+    installed in this image). Without a GPU the driver must refuse to sample: there is no CPU path behind the shim
+    either. tests/test_gpu_shim.py runs it on the GPU box."""
+    import subprocess
+    exe = str(tmp_path / "shim_driver")
+    r = build_shim_driver(exe)
     assert r.returncode == 0, r.stderr
+    import elections_dtree_b200._native as N
+    if N.lib().dtree_device_count() == 0:
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode != 0 and "no CPU path" in run.stderr
 
 
 def test_update_property_random_ballot_streams(pkg, port):
