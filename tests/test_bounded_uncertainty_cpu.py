@@ -6,9 +6,13 @@ candidate is weakest. The model keeps what makes the rule exact on the GPU — a
   eager      split everything an elimination releases before deciding the next round (irv_ballot.cpp:86-133 on a
              lazily expanded tree; what deferred_kernel did before, and what simulate_kernel's materialisation implies)
   heaviest   lane_kernel's order: split the waiting node with the most ballots until the round is implied
-  threshold  deferred_kernel's order: split every waiting node holding at least need / (2 n_waiting) + 1 ballots
+  threshold  deferred_kernel's round-1 order: split every waiting node holding at least need / (2 n_waiting) + 1 ballots
+  histogram  deferred_kernel's order now: waiting ballots are counted per weight class (2^b <= ballots < 2^(b+1));
+             every node of weight >= 2^b is split for the largest b whose lighter classes together hold at most 3/4 of
+             the margin the round is missing (with nothing to spare, everything); single-ballot nodes wait apart and
+             are touched only then
 
-All three must give the same elimination order in every election, including ties (broken by a per-round draw that is
+All of them must give the same elimination order in every election, including ties (broken by a per-round draw that is
 a pure function of the seed), near-ties and elections with a handful of ballots. No GPU, no library: host logic only.
 """
 import hashlib
@@ -60,8 +64,21 @@ class Election:
         elif self.policy == "heaviest":
             i = max(range(len(self.waiting)), key=lambda j: self.waiting[j][1])
             todo = [self.waiting.pop(i)]
-        else:  # threshold
+        elif self.policy == "threshold":
             tau = need // (2 * max(len(self.waiting), 1)) + 1
+            todo = [w for w in self.waiting if w[1] >= tau]
+            self.waiting = [w for w in self.waiting if w[1] < tau]
+            assert todo
+        else:  # histogram (deferred.cuh: hist[], tau_quarters = 3)
+            hist = [0] * 32
+            for _, n in self.waiting:
+                hist[n.bit_length() - 1] += n
+            allow, below, cls = (need * 3) >> 2, 0, 0
+            for b in range(32):
+                if b == 0 or below <= allow:
+                    cls = b
+                below += hist[b]
+            tau = 1 if cls == 0 else 1 << cls
             todo = [w for w in self.waiting if w[1] >= tau]
             self.waiting = [w for w in self.waiting if w[1] < tau]
             assert todo
@@ -98,17 +115,18 @@ class Election:
                                                          (6, 3, 500, 1.0), (8, 8, 1_000_000, 0.8), (7, 7, 300, 0.9),
                                                          (10, 10, 1_000_000, 0.5), (9, 9, 5_000, 1.0)])
 def test_lazy_rounds_give_the_eager_elimination_order(nc, max_depth, n_ballots, skew):
-    saved = {"heaviest": 0, "threshold": 0}
+    saved = {"heaviest": 0, "threshold": 0, "histogram": 0}
     eager_splits = 0
     for seed in range(60):
         want = Election(seed, nc, max_depth, n_ballots, skew, "eager")
         order = want.run()
         assert sorted(order) == list(range(nc))
         eager_splits += want.splits
-        for policy in ("heaviest", "threshold"):
+        for policy in ("heaviest", "threshold", "histogram"):
             e = Election(seed, nc, max_depth, n_ballots, skew, policy)
             assert e.run() == order, (seed, policy)
             assert e.splits <= want.splits
             saved[policy] += want.splits - e.splits
     if n_ballots >= 100_000 and skew < 1.0:  # lopsided elections: most of the tree never has to be looked at
         assert saved["heaviest"] > 0.5 * eager_splits and saved["threshold"] > 0.3 * eager_splits, (saved, eager_splits)
+        assert saved["histogram"] >= saved["threshold"], saved  # the histogram rule never splits more than the old one here

@@ -20,6 +20,20 @@ for nc, mn, mx, a0, vd in ((6, 0, 6, 1.0, False), (14, 1, 9, 0.5, True), (27, 0,
         if ref is None:
             ref = (w, o)
         assert ref[0].tolist() == w.tolist() and np.array_equal(ref[1], o)
+    # the overflow paths: arenas of 8 records, so that elections re-run in the shared worst-case arenas (try-lock)
+    # and lane_kernel hands them to its replay launch; a split budget of 1; the three tree-build paths; plurality
+    t.tune(arena_cap=8)
+    for mode in (1, 2):
+        t.tune(mode=mode)
+        w, o = t.sample_posterior_counts(96, 1500, seed="SAN", return_orders=True)
+        assert ref[0].tolist() == w.tolist() and np.array_equal(ref[1], o)
+    t.tune(arena_cap=0, mode=2, lane_max_splits=1)
+    assert t.sample_posterior_counts(96, 1500, seed="SAN").tolist() == ref[0].tolist()
+    t.tune(lane_max_splits=-1, mode=-1)
+    for bm in (1, 2, 0):
+        t.tune(build_mode=bm)
+        assert t.sample_posterior_counts(96, 1500, seed="SAN").tolist() == ref[0].tolist()
+    assert int(t.sample_posterior_counts(96, 1500, seed="SAN", sc_function="plurality").sum()) >= 96
     p, off, cnt = t.posterior_set_indices(3, 1500, False, "SAN")
     assert int(cnt.sum()) == 1500
     order, ties = pkg.irv_indices(p, off, cnt, nc, "s", 0)
