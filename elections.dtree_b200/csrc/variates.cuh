@@ -243,8 +243,7 @@ __device__ __forceinline__ uint32_t binv(uint32_t n, float ps, uint32_t bits) {
 // n p q), else if v alpha / (a/us^2 + b) <= f(k)/f(m), m the mode.
 struct Btrs32 {
   float nf, p, spq, b, a, c, vr, npq;
-  double np_d;  // n p in double: k - n p is where f32 would cancel
-  uint32_t n, m;
+  uint32_t n;
 };
 
 __device__ __forceinline__ Btrs32 btrs32_setup(uint32_t n, float ps) {
@@ -259,8 +258,6 @@ __device__ __forceinline__ Btrs32 btrs32_setup(uint32_t n, float ps) {
   s.a = __fmaf_rn(0.01f, ps, __fmaf_rn(0.0248f, s.b, -0.0873f));
   s.c = __fmaf_rn(s.nf, ps, 0.5f);
   s.vr = __fadd_rn(0.92f, -__fdividef(4.2f, s.b));
-  s.np_d = __dmul_rn((double)n, (double)ps);
-  s.m = (uint32_t)__dadd_rn(s.np_d, (double)ps);  // the mode floor((n+1) p) = floor(n p + p)
   return s;
 }
 
@@ -291,7 +288,7 @@ __device__ __forceinline__ float stirlerr32(float x) {
 // x log(x / mu) + mu - x from dx = x - mu (formed without cancellation by the caller) and s = x + mu: Loader's series
 // in v = dx / s, 10 terms; *av = |v| tells the caller whether it has converged (|v| <= 0.4: remainder < 1e-8 relative).
 __device__ __forceinline__ float bd0_32(float x, float dx, float s, float &av) {
-  const float v = __fdiv_rn(dx, s), v2 = __fmul_rn(v, v);
+  const float v = __fdividef(dx, s), v2 = __fmul_rn(v, v);
   av = fabsf(v);
   float t = 4.76190476e-2f;            // 1/21
   t = __fmaf_rn(t, v2, 5.26315789e-2f);  // 1/19
@@ -305,31 +302,45 @@ __device__ __forceinline__ float bd0_32(float x, float dx, float s, float &av) {
   t = __fmaf_rn(t, v2, 0.333333333f);    // 1/3
   return __fmaf_rn(dx, v, __fmul_rn(__fmul_rn(2.0f, x), __fmul_rn(__fmul_rn(v, v2), t)));
 }
+// The same at the mode, where |dx| <= 1 and mu >= 30: v <= 1/60 and one term of the series is exact to 1e-8.
+__device__ __forceinline__ float bd0_near(float x, float dx, float s) {
+  const float v = __fdividef(dx, s);
+  return __fmaf_rn(dx, v, __fmul_rn(__fmul_rn(0.666666687f, x), __fmul_rn(__fmul_rn(v, v), v)));
+}
 
 // The BTRS acceptance test  log(v alpha / (a/us^2 + b)) <= log(f(k)/f(m))  at f32 precision.
 // log f(k) - log f(m) is evaluated in Loader's saddle-point form (the one R's dbinom uses),
 //   1/2 log(m (n-m) / (k (n-k))) - [stirlerr(k) + stirlerr(n-k) - stirlerr(m) - stirlerr(n-m)]
 //       - [bd0(k, np) + bd0(n-k, nq) - bd0(m, np) - bd0(n-m, nq)],
-// every term of which is small and free of cancellation once k - np and m - np have been formed in double; the
-// result is within 1.1e-5 of the double-precision value over 1.3 M (n, p, k) cases with n < 2^20, n p >= 30
-// (measured: 3 % of the guard band used below). Returns 1 accept, 0 reject, -1 undecided: inside the guard band, or
-// too far in a tail for the series (|k - np| > 0.4 (k + np)); the caller then asks btrs_accept. Out of line: reached
-// by ~15-45 % of the proposals only, and one copy keeps the kernels' hot loops inside the instruction cache.
+// every term of which is small and free of cancellation once k - np and m - np have been formed in double. With
+// 2-ulp divisions the result stays within 1.4e-5 of the double-precision value over 1.3 M (n, p, k) cases with
+// n < 2^20, n p >= 30 (6 % of the guard band used below). Returns 1 accept, 0 reject, -1 undecided: inside the guard
+// band, or too far in a tail for the series (|k - np| > 0.4 (k + np)); the caller then asks btrs_accept. Out of line:
+// reached by 15-45 % of the proposals only, and one copy keeps the kernels' hot loops inside the instruction cache.
+// (Tried in front of it and dropped: the 12-operation squeeze of Kachitvichyanukul & Schmeiser 1988, step 5.2. It
+// settles all but ~2/sqrt(npq) of the proposals, but a warp runs both tests as soon as one lane needs the second:
+// 0.86 ms against 0.83 ms per 100 000 C3 elections.)
 static __device__ __noinline__ int btrs32_accept(const Btrs32 &s, float us, float v, float kd) {
   const uint32_t k = (uint32_t)kd;
   if (k == 0u || k >= s.n) return -1;
   const float alpha = __fmul_rn(__fadd_rn(2.83f, __fdividef(5.1f, s.b)), s.spq);
-  const float vv = __fdiv_rn(__fmul_rn(v, alpha), __fadd_rn(__fdiv_rn(s.a, __fmul_rn(us, us)), s.b));
+  const float vv = __fdividef(__fmul_rn(v, alpha), __fadd_rn(__fdividef(s.a, __fmul_rn(us, us)), s.b));
   const float lv = logf(vv);
-  const float dxk = (float)__dadd_rn((double)k, -s.np_d), dxm = (float)__dadd_rn((double)s.m, -s.np_d);
-  const float kf = kd, mf = (float)s.m, nk = (float)(s.n - k), nm = (float)(s.n - s.m);
-  const float npf = (float)s.np_d, nqf = (float)__dadd_rn((double)s.n, -s.np_d);
-  const float delta = (float)((int)k - (int)s.m);
-  const float half = __fmul_rn(0.5f, __fadd_rn(log1pf(-__fdiv_rn(delta, kf)), log1pf(__fdiv_rn(delta, nk))));
+  // n p in double: k - n p and m - n p are where f32 would cancel. m = floor((n+1) p) = floor(n p + p) is the mode,
+  // formed exactly as btrs_accept forms it.
+  const double np_d = __dmul_rn((double)s.n, (double)s.p);
+  const uint32_t m = (uint32_t)__dadd_rn(np_d, (double)s.p);
+  const float dxk = (float)__dadd_rn((double)k, -np_d), dxm = (float)__dadd_rn((double)m, -np_d);
+  const float kf = kd, mf = (float)m, nk = (float)(s.n - k), nm = (float)(s.n - m);
+  const float npf = (float)np_d, nqf = (float)__dadd_rn((double)s.n, -np_d);
+  const float delta = (float)((int)k - (int)m);
+  // 1/2 [log(1 - delta/k) + log(1 + delta/(n-k))] as one log1p of a + b + a b
+  const float ra = -__fdividef(delta, kf), rb = __fdividef(delta, nk);
+  const float half = __fmul_rn(0.5f, log1pf(__fadd_rn(__fadd_rn(ra, rb), __fmul_rn(ra, rb))));
   const float st = __fadd_rn(__fadd_rn(stirlerr32(kf), stirlerr32(nk)), -__fadd_rn(stirlerr32(mf), stirlerr32(nm)));
-  float v1, v2, v3, v4;
+  float v1, v2;
   const float bd = __fadd_rn(__fadd_rn(bd0_32(kf, dxk, __fadd_rn(kf, npf), v1), bd0_32(nk, -dxk, __fadd_rn(nk, nqf), v2)),
-                             -__fadd_rn(bd0_32(mf, dxm, __fadd_rn(mf, npf), v3), bd0_32(nm, -dxm, __fadd_rn(nm, nqf), v4)));
+                             -__fadd_rn(bd0_near(mf, dxm, __fadd_rn(mf, npf)), bd0_near(nm, -dxm, __fadd_rn(nm, nqf))));
   if (fmaxf(v1, v2) > 0.4f) return -1;
   const float lf = __fadd_rn(__fadd_rn(half, -st), -bd);
   const float guard = __fmaf_rn(8e-6f, fabsf(lf) + fabsf(lv), 3e-5f);

@@ -15,7 +15,7 @@ for case in cases:
     cfg = dict(W.CONFIGS[name])
     nc = cfg["n_candidates"]
     if "g" in case:
-        gamma = {"g005": 0.05, "g02": 0.2, "g0": 0.0}[case[2:]]
+        gamma = {"g005": 0.05, "g02": 0.2, "g0": 0.0, "g01": 0.1, "g03": 0.3}[case[2:]]
         prefs, offsets = W.plackett_luce_ballots(nc, gamma, cfg["observed"][2], cfg["observed"][3])
     else:
         prefs, offsets = W.observed_ballots(name)
@@ -38,6 +38,7 @@ for case in cases:
         r = {"case": case, "mode": st["mode"], key: v, "elections": n, "ms": round(best * 1e3, 2),
              "elections_per_s": round(n / best), "splits_per_election": round(st["items"] / n, 1),
              "records_rw_per_election": round((st["entries"] + st["irv_rereads"]) / n, 1),
+             "urn_splits_per_election": round(st["urn_items"] / n, 1), "gammas_per_election": round(st["gammas"] / n, 1),
              "retries": st["lane_retries"], "arena_runs": st["arena_runs"], "scratch_GB": round(st["scratch_bytes"] / 1e9, 2)}
         rows.append(r)
         print(json.dumps(r), flush=True)
