@@ -40,7 +40,7 @@ from __graft_entry__ import load_pkg  # noqa: E402
 
 METRIC = "simulated IRV elections/sec"
 SEED = "BENCHSEEDx"
-DEFAULT_EPG = {"C1": 4_000_000, "C2": 1_000_000, "C3": 100_000, "C4": 4_000, "C5": 200_000}
+DEFAULT_EPG = {"C1": 4_000_000, "C2": 1_000_000, "C3": 100_000, "C4": 9_472, "C5": 200_000}  # C4: 4 waves of 2 368 warps
 KERNELS = {0: "simulate_kernel", 1: "deferred_kernel", 2: "lane_kernel"}
 
 
@@ -429,7 +429,7 @@ def main():
         c3close = dict(W.CONFIGS["C3"])
         c3close["observed"] = ("pl", 0.05) + tuple(c3close["observed"][2:])
         todo = [("C1", dict(W.CONFIGS["C1"]), 4_000_000, 592), ("C2", dict(W.CONFIGS["C2"]), 1_000_000, 592),
-                ("C4", dict(W.CONFIGS["C4"]), 4_000, 148), ("C5", dict(W.CONFIGS["C5"]), 200_000, 592),
+                ("C4", dict(W.CONFIGS["C4"]), DEFAULT_EPG["C4"], 148), ("C5", dict(W.CONFIGS["C5"]), 200_000, 592),
                 ("C3 shape, gamma=0.05 (close race)", c3close, 20_000, 296)]
         for wname, wcfg, w_epg, mat_el in todo:
             wt_, _ = make_tree(wname.split(" ")[0], wcfg)
