@@ -757,7 +757,12 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
         const uint64_t warp_elections = (uint64_t)pl.blocks_per_sm * t->sm_count * (pl.block / 32);
         // ... and the elections are light: a heavy election (a close race expands tens of thousands of nodes) is
         // better served by the 32 lanes and shared-memory tile of deferred_kernel than by one thread.
-        want_lane = lane_threads >= 16 * warp_elections && (uint64_t)(n_elections - pilot_done) * 10 >= lane_threads * 7 &&
+        // A launch of either kernel lasts about as long as its slowest warp: lane_kernel ~ one batch of 32 elections
+        // per warp however few elections there are, deferred_kernel ~ one election per warp and wave. Measured on the
+        // 10-candidate benchmark a lane batch on a partly filled machine takes as long as 3.5 waves of deferred_kernel
+        // (0.51 ms vs 0.144 ms), so the thread-per-election kernel wins from about four waves' worth of elections up
+        // (9 500), well before the machine is full (12 500 elections per GPU: 0.73 ms with a warp each).
+        want_lane = lane_threads >= 16 * warp_elections && (uint64_t)(n_elections - pilot_done) >= 4 * warp_elections &&
                     z.nodes_per_election <= 5000.0;
       }
     }
