@@ -108,16 +108,18 @@ __device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<B
     stat[kStatUrnItems] += 1;
     if (f.node >= 0) stat[kStatSlots] += lv.d;
     const uint64_t picks = urn_picks(a, lv, f.node, nbase, f.count, key, f.node_key);
-    uint32_t done = 0;  // bit b set: ball b already grouped with an earlier ball of the same outcome
+    // balls per outcome, 4 bits each (count <= 8, at most 33 outcomes); an outcome is emitted when its first ball
+    // comes by and its counter is cleared, so every outcome is handled once without comparing balls pairwise
+    uint64_t c4[3] = {0ull, 0ull, 0ull};
     for (uint32_t b = 0; b < f.count; ++b) {
-      if (done >> b & 1u) continue;
+      const uint32_t s = (uint32_t)(picks >> (8u * b)) & 0xFFu;
+      c4[s >> 4] += 1ull << (4u * (s & 15u));
+    }
+    for (uint32_t b = 0; b < f.count; ++b) {
       const uint32_t slot = (uint32_t)(picks >> (8u * b)) & 0xFFu;
-      uint32_t c = 1;
-      for (uint32_t b2 = b + 1; b2 < f.count; ++b2)
-        if (((uint32_t)(picks >> (8u * b2)) & 0xFFu) == slot) {
-          ++c;
-          done |= 1u << b2;
-        }
+      const uint32_t c = (uint32_t)(c4[slot >> 4] >> (4u * (slot & 15u))) & 15u;
+      if (c == 0u) continue;
+      c4[slot >> 4] &= ~(15ull << (4u * (slot & 15u)));
       BallotKey<W> pk = f.prefix;
       uint32_t cand = 0;
       const bool stop = slot == lv.K;  // only possible when lv.T
