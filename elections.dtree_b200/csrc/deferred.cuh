@@ -283,7 +283,9 @@ __device__ void deferred_resolve(const SimArgs &a, WarpTile<1> &wt, DeferredWarp
         atomicSub(&ws.hist[0], 1u);
         // (walking a single ballot's chain on in this lane until a standing candidate takes it was measured again in
         // round 2: 53.6 k -> 89 k splits per C4 election, 36 k -> 30 k elections/s. One hop per waiting ballot usually
-        // settles the round; the hops below it are never needed.)
+        // settles the round; the hops below it are never needed. Also measured and dropped: listing the children of the
+        // batch's nodes in shared memory and routing them cooperatively, 32 at a time, with one reservation per
+        // destination — bit-identical, but batches are too small to pay for the second phase: 36 k -> 24 k.)
         split_small_node(a, ws, sc, cp, x, eliminated, key, stat);
       }
       __syncwarp();
