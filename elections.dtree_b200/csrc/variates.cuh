@@ -86,12 +86,12 @@ __device__ __forceinline__ bool gamma_attempt(const GammaShape &s, const U4 r, f
   const float x = __fmul_rn(rad, __cosf(__fmul_rn(6.28318548f, u01f(r.y))));
   const float w = __fmul_rn(s.c, x);
   float v = __fmaf_rn(s.c, x, 1.0f);
-  if (v <= 0.0f) return false;
+  if (__builtin_expect(v <= 0.0f, 0)) return false;
   v = __fmul_rn(__fmul_rn(v, v), v);
   const float u = u01f(r.z);
   const float x2 = __fmul_rn(x, x);
   g = __fmul_rn(s.d, v);
-  if (u < __fmaf_rn(-0.0331f, __fmul_rn(x2, x2), 1.0f)) return true;
+  if (__builtin_expect(u < __fmaf_rn(-0.0331f, __fmul_rn(x2, x2), 1.0f), 1)) return true;
   if (!EXACT_ONLY) {
     // log u < x^2/2 + d (1 - v + log v) in f32. With w = c x: 1 - v + log v = -4.5 w^2 + S(w),
     // S(w) = sum_{n>=4} 3 (-1)^(n+1) w^n / n, and 4.5 d c^2 = 1/2, so the right-hand side is d S(w) up to the
@@ -117,8 +117,8 @@ __device__ __forceinline__ bool gamma_attempt(const GammaShape &s, const U4 r, f
       rhs = __fmaf_rn(s.d, __fadd_rn(__fadd_rn(1.0f, -v), logf(v)), __fmul_rn(0.5f, x2));
       guard = __fmaf_rn(2e-5f, fabsf(rhs) + fabsf(lu), 3e-4f);
     }
-    if (lu < __fadd_rn(rhs, -guard)) return true;
-    if (lu > __fadd_rn(rhs, guard)) return false;
+    if (__builtin_expect(lu < __fadd_rn(rhs, -guard), 1)) return true;
+    if (__builtin_expect(lu > __fadd_rn(rhs, guard), 1)) return false;
   }
   return gamma_accept_exact(s.c, x, s.d, u);
 }
@@ -145,7 +145,7 @@ __device__ __forceinline__ float gamma_variate(float alpha, RngKey key, uint64_t
     ++attempts;
     boost_bits = r.w;
     if (gamma_attempt<EXACT_ONLY>(s, r, g)) break;
-    if (attempt > 64u) {  // unreachable in practice (acceptance > 0.95); bounds the loop
+    if (__builtin_expect(attempt > 64u, 0)) {  // unreachable in practice (acceptance > 0.95); bounds the loop
       g = s.d;
       break;
     }
@@ -180,7 +180,7 @@ static __device__ __noinline__ float gamma_big(double alpha, RngKey key, uint64_
 template <bool LOG>
 __device__ __forceinline__ float outcome_gamma(uint32_t count, float a_prior, RngKey key, uint64_t node_key, uint32_t slot,
                                                uint32_t &n_drawn) {
-  if (count >= (1u << 22)) {
+  if (__builtin_expect(count >= (1u << 22), 0)) {
     ++n_drawn;
     return gamma_big<LOG>((double)count + (double)a_prior, key, node_key, slot);
   }
@@ -391,7 +391,7 @@ __device__ __forceinline__ uint32_t binomial_small_p(uint32_t n, float ps, RngKe
     ++attempts;
     return binv(n, ps, r.x);
   }
-  if (n < (1u << 20)) {
+  if (__builtin_expect(n < (1u << 20), 1)) {
     const Btrs32 s = btrs32_setup(n, ps);
     for (uint32_t attempt = 0;; ++attempt) {
       const U4 r = node_random(key, node_key, kStreamBinomial + slot, attempt);
@@ -403,11 +403,11 @@ __device__ __forceinline__ uint32_t binomial_small_p(uint32_t n, float ps, RngKe
         if (us >= 0.07f && v <= s.vr) return (uint32_t)kd;
         if (kd < 0.0f || kd > s.nf) continue;
         int ok = EXACT_ONLY ? -1 : btrs32_accept(s, us, v, kd);
-        if (ok < 0)
+        if (__builtin_expect(ok < 0, 0))
           ok = btrs_accept((double)n, (double)ps, (double)s.spq, (double)s.b, (double)s.a, (double)us, (double)v, (double)kd) ? 1 : 0;
         if (ok) return (uint32_t)kd;
       }
-      if (attempt > 256u) return (uint32_t)__fmul_rn(nf, ps);  // unreachable in practice
+      if (__builtin_expect(attempt > 256u, 0)) return (uint32_t)__fmul_rn(nf, ps);  // unreachable in practice
     }
   }
   return binomial_btrs64(n, ps, key, node_key, slot, attempts);
