@@ -160,3 +160,55 @@ def test_plurality_on_the_device_is_bit_exact(pkg, L, nc, mn, mx, a0, vd, n_obs,
     assert (a.astype(np.int64) + b.astype(np.int64)).tolist() == want.tolist()
     with pytest.raises(NotImplementedError):
         t.sample_posterior_counts(10, n_ballots, replace=replace, seed="PLUR", sc_function="stv")
+
+
+def test_random_configurations_agree_across_kernels_and_tunings(pkg, L):
+    """60 random small configurations (2..14 candidates, every combination of min/max depth, a0 from 0 to 5, vd,
+    replace, empty to dense trees, 0..6000 ballots) x the three kernels x random arena caps, split budgets, urn limits
+    and resolve thresholds: elimination orders and win counts must be identical to the materialising kernel's, and
+    win counts must add up. A cheap net under everything the tunings can reach."""
+    import warnings
+    rng = np.random.default_rng(2024)
+    W = pkg.workloads
+    for case in range(60):
+        nc = int(rng.integers(2, 15))
+        mx = int(rng.integers(1, nc + 1))
+        mn = int(rng.integers(0, mx + 1))
+        a0 = float(rng.choice([0.0, 1e-3, 0.3, 1.0, 5.0]))
+        vd = bool(rng.integers(0, 2)) and mx >= 1
+        replace = bool(rng.integers(0, 2))
+        n_obs = int(rng.choice([0, 1, 7, 60, 400]))
+        t = pkg.dirichlet_tree(W.candidate_names(nc), mn, mx, a0, vd, device=0)
+        if n_obs:
+            pmf = rng.random(nc + 1) + 0.05
+            prefs, offsets = W.plackett_luce_ballots(nc, float(rng.choice([0.0, 0.3, 1.0])), n_obs, 100 + case, pmf)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                t.update_indices(prefs, offsets)
+        n_ballots = n_obs + int(rng.choice([0, 1, 9, 300, 6000]))
+        if n_ballots == 0:
+            n_ballots = 1
+        nw = int(rng.integers(1, nc)) if nc > 2 else 1
+        n_el = 160
+        t.tune(mode=0, arena_cap=0, lane_max_splits=-1, urn_max=8, tau_quarters=3)
+        want_w, want_o = t.sample_posterior_counts(n_el, n_ballots, n_winners=nw, replace=replace, seed="RND%d" % case,
+                                                   return_orders=True)
+        assert int(want_w.sum()) == n_el * nw
+        for mode in (1, 2):
+            t.tune(mode=mode, arena_cap=int(rng.choice([0, 8, 40])), lane_max_splits=int(rng.choice([-1, 0, 1, 6])),
+                   urn_max=int(rng.choice([8, 8, 3, 0])), tau_quarters=int(rng.integers(1, 4)))
+            # the urn limit changes which sampler a node uses, hence the draws: compare within the same urn_max
+            um = int(rng.choice([8, 8, 8, 2]))
+            t.tune(urn_max=um)
+            if um != 8:
+                t.tune(mode=0, arena_cap=0)
+                ref_w, ref_o = t.sample_posterior_counts(n_el, n_ballots, n_winners=nw, replace=replace,
+                                                         seed="RND%d" % case, return_orders=True)
+                t.tune(mode=mode)
+            else:
+                ref_w, ref_o = want_w, want_o
+            w, o = t.sample_posterior_counts(n_el, n_ballots, n_winners=nw, replace=replace, seed="RND%d" % case,
+                                             return_orders=True)
+            assert w.tolist() == ref_w.tolist() and np.array_equal(o, ref_o), (case, mode, nc, mn, mx, a0, vd, replace, n_obs, n_ballots)
+            w2 = t.sample_posterior_counts(n_el, n_ballots, n_winners=nw, replace=replace, seed="RND%d" % case)
+            assert w2.tolist() == ref_w.tolist(), (case, mode)
