@@ -502,10 +502,10 @@ void begin_call_stats(dtree *t) {
 
 // Waits for the stream, fetches the result block with one copy and digests it: kernel-side failure, counters,
 // arena usage (which grows the cached sizing if an election came close to its capacity).
-int fetch_results(dtree *t, cudaStream_t s) {
+int fetch_results(dtree *t, cudaStream_t s, bool copy_enqueued = false) {
   NvtxRange nv("dtree:read_back");
   HostTimer tm;
-  CUDA_TRY(cudaMemcpyAsync(t->h_res, t->d_res.p, sizeof(ResultBlock), cudaMemcpyDeviceToHost, s));
+  if (!copy_enqueued) CUDA_TRY(cudaMemcpyAsync(t->h_res, t->d_res.p, sizeof(ResultBlock), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   t->stats[kOutD2H] += sizeof(ResultBlock);
   t->stats[kOutFinishUs] += tm.us();
@@ -1347,10 +1347,18 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
   // collect — also on failure, so that nothing is left running when the call returns
   std::string first_error = rc ? g_error : std::string();
   uint64_t launches = 0;
-  for (Job &j : jobs) {
+  std::vector<char> enqueued(jobs.size(), 0);
+  for (size_t k = 0; k < jobs.size(); ++k) {  // every device's read-back is in flight before the first one is waited for
+    dtree *r = jobs[k].t;
+    DeviceGuard g(r->device);
+    enqueued[k] = cudaMemcpyAsync(r->h_res, r->d_res.p, sizeof(ResultBlock), cudaMemcpyDeviceToHost, jobs[k].s) == cudaSuccess;
+    if (!enqueued[k]) cudaGetLastError();
+  }
+  for (size_t k = 0; k < jobs.size(); ++k) {
+    Job &j = jobs[k];
     dtree *r = j.t;
     DeviceGuard g(r->device);
-    int rc2 = fetch_results(r, j.s);
+    int rc2 = fetch_results(r, j.s, enqueued[k] != 0);
     if (rc2 == DTREE_OK && rc == DTREE_OK)
       for (uint32_t c = 0; c < nc; ++c) win_counts[c] += r->h_res->wins[c];
     else if (rc == DTREE_OK) {
