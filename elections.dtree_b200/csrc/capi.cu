@@ -192,6 +192,7 @@ struct dtree {
   int64_t lane_max_splits = -1;  // lane_kernel hands an election to the replay after this many splits (-1 auto, 0 never)
   uint32_t tau_quarters = 3;     // deferred_kernel's resolve threshold (deferred.cuh)
   uint32_t binv_max = 30;        // binomials with n p below this use inversion, the others BTRS
+  uint32_t last_lane_retries = 0;  // elections lane_kernel handed to its replay in the last call read back
   uint64_t mem_avail = 0;        // device bytes the plans may use (free + held by this handle), as last queried
   int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
   // replicas on other devices for dtree_sample_posterior_multi (owned; same parameters, tree copied when stale)
@@ -526,6 +527,7 @@ int fetch_results(dtree *t, cudaStream_t s, bool copy_enqueued = false) {
     }
     t->stats[kOutArenaRuns] = R.usage[3];
     t->stats[kOutLaneRetries] = R.usage[4];
+    t->last_lane_retries = R.usage[4];
   }
   return DTREE_OK;
 }
@@ -854,6 +856,10 @@ int job_launch_wave(Job &j) {
     Plan replay = j.pp;
     replay.deferred = true;
     replay.lane = false;
+    // The replay's warps pull elections from the retry list until it is empty, so any grid is correct; it is sized
+    // for four times what the previous call handed over (+ 64 elections), not for a full machine that usually finds
+    // the list empty.
+    replay.grid = (int)std::min<uint64_t>((uint64_t)replay.grid, (4ull * t->last_lane_retries + 64 + 3) / 4);
     CUDA_TRY(launch(replay, ar, j.s));
     ++j.launches;
   }

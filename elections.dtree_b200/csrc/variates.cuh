@@ -98,7 +98,7 @@ __device__ __forceinline__ bool gamma_attempt(const GammaShape &s, const U4 r, f
     // rounding of c (|x^2 eps_c| <= 1.6e-5, inside the guard). The series is used where it converges fast
     // (|w| < 1/4, i.e. every large shape, where the direct form cancels catastrophically); elsewhere d < 60 and
     // the direct form is accurate.
-    const float lu = logf(u);
+    const float lu = __logf(u);  // absolute error 2^-21 near 1, 3 ulp (< 6e-6) elsewhere: inside the guards below
     float rhs, guard;
     if (fabsf(w) < 0.25f) {
       float p = -0.25f;                       // -3/12
@@ -282,7 +282,7 @@ static __device__ const float kStirlErr[16] = {0.0f, 0.0810614668f, 0.0413406960
 __device__ __forceinline__ float stirlerr32(float x) {
   if (x < 16.0f) return kStirlErr[(int)x];
   const float r = __fdividef(1.0f, x), r2 = __fmul_rn(r, r);
-  return __fmul_rn(r, __fmaf_rn(-r2, __fmaf_rn(-r2, 7.93650794e-4f, 2.77777778e-3f), 8.33333333e-2f));
+  return __fmul_rn(r, __fmaf_rn(-r2, 2.77777778e-3f, 8.33333333e-2f));  // next term: 1/(1260 x^5) < 1e-9 here
 }
 
 // x log(x / mu) + mu - x from dx = x - mu (formed without cancellation by the caller) and s = x + mu: Loader's series
@@ -290,6 +290,10 @@ __device__ __forceinline__ float stirlerr32(float x) {
 __device__ __forceinline__ float bd0_32(float x, float dx, float s, float &av) {
   const float v = __fdividef(dx, s), v2 = __fmul_rn(v, v);
   av = fabsf(v);
+  if (v2 < 2.5e-3f) {  // |v| < 0.05, the usual case away from small n p: three terms leave a remainder < 1e-9 relative
+    const float t3 = __fmaf_rn(__fmaf_rn(0.142857143f, v2, 0.2f), v2, 0.333333333f);
+    return __fmaf_rn(dx, v, __fmul_rn(__fmul_rn(2.0f, x), __fmul_rn(__fmul_rn(v, v2), t3)));
+  }
   float t = 4.76190476e-2f;            // 1/21
   t = __fmaf_rn(t, v2, 5.26315789e-2f);  // 1/19
   t = __fmaf_rn(t, v2, 5.88235294e-2f);  // 1/17
@@ -313,8 +317,8 @@ __device__ __forceinline__ float bd0_near(float x, float dx, float s) {
 //   1/2 log(m (n-m) / (k (n-k))) - [stirlerr(k) + stirlerr(n-k) - stirlerr(m) - stirlerr(n-m)]
 //       - [bd0(k, np) + bd0(n-k, nq) - bd0(m, np) - bd0(n-m, nq)],
 // every term of which is small and free of cancellation once k - np and m - np have been formed in double. With
-// 2-ulp divisions the result stays within 1.4e-5 of the double-precision value over 1.3 M (n, p, k) cases with
-// n < 2^20, n p >= 30 (6 % of the guard band used below). Returns 1 accept, 0 reject, -1 undecided: inside the guard
+// 2-ulp divisions and __logf (absolute error 2^-21) the result stays within 1.5e-5 of the double-precision value over
+// 1.3 M (n, p, k) cases with n < 2^20, n p >= 30 (7 % of the guard band used below). Returns 1 accept, 0 reject, -1 undecided: inside the guard
 // band, or too far in a tail for the series (|k - np| > 0.4 (k + np)); the caller then asks btrs_accept. Out of line:
 // reached by 15-45 % of the proposals only, and one copy keeps the kernels' hot loops inside the instruction cache.
 // (Tried in front of it and dropped: the 12-operation squeeze of Kachitvichyanukul & Schmeiser 1988, step 5.2. It
@@ -325,7 +329,7 @@ static __device__ __noinline__ int btrs32_accept(const Btrs32 &s, float us, floa
   if (k == 0u || k >= s.n) return -1;
   const float alpha = __fmul_rn(__fadd_rn(2.83f, __fdividef(5.1f, s.b)), s.spq);
   const float vv = __fdividef(__fmul_rn(v, alpha), __fadd_rn(__fdividef(s.a, __fmul_rn(us, us)), s.b));
-  const float lv = logf(vv);
+  const float lv = __logf(vv);  // absolute error 2^-21 near 1, 3 ulp elsewhere: 1/10 of the guard band
   // n p in double: k - n p and m - n p are where f32 would cancel. m = floor((n+1) p) = floor(n p + p) is the mode,
   // formed exactly as btrs_accept forms it.
   const double np_d = __dmul_rn((double)s.n, (double)s.p);
@@ -336,7 +340,7 @@ static __device__ __noinline__ int btrs32_accept(const Btrs32 &s, float us, floa
   const float delta = (float)((int)k - (int)m);
   // 1/2 [log(1 - delta/k) + log(1 + delta/(n-k))] as one log1p of a + b + a b
   const float ra = -__fdividef(delta, kf), rb = __fdividef(delta, nk);
-  const float half = __fmul_rn(0.5f, log1pf(__fadd_rn(__fadd_rn(ra, rb), __fmul_rn(ra, rb))));
+  const float half = __fmul_rn(0.5f, __logf(__fadd_rn(1.0f, __fadd_rn(__fadd_rn(ra, rb), __fmul_rn(ra, rb)))));
   const float st = __fadd_rn(__fadd_rn(stirlerr32(kf), stirlerr32(nk)), -__fadd_rn(stirlerr32(mf), stirlerr32(nm)));
   float v1, v2;
   const float bd = __fadd_rn(__fadd_rn(bd0_32(kf, dxk, __fadd_rn(kf, npf), v1), bd0_32(nk, -dxk, __fadd_rn(nk, nqf), v2)),
