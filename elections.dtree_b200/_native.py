@@ -8,7 +8,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdtree_b200.so")
+# DTREE_B200_LIB selects another build of the same library (profiling variants); there is still no fallback.
+LIB_PATH = os.environ.get("DTREE_B200_LIB") or os.path.join(_HERE, "lib", "libdtree_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_ABORTED = 0, 1, 2, 3, 4

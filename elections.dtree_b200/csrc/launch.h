@@ -16,9 +16,6 @@ struct LaunchCfg {
 constexpr int kBlockSizes[] = {32, 64, 128, 256};
 constexpr int kNumBlockSizes = 4;
 
-// All shared memory of simulate_kernel is static (per-warp tiles); nothing dynamic to request.
-inline size_t simulate_smem_bytes(uint32_t, int) { return 0; }
-
 // Launches simulate_kernel<W, block, log>. Returns cudaErrorInvalidValue for an unsupported block size.
 template <int W>
 cudaError_t launch_simulate(const SimArgs &a, const LaunchCfg &cfg);

@@ -25,6 +25,19 @@
 
 namespace dtb {
 
+// Profiling build (-DDTB_PHASE_CLOCKS): lane 0 of every warp accumulates the cycles (in units of 64) it spends in the
+// small-item walk, the big-item chunks, the barrier at the end of a level and the IRV stage; simulate_kernel reports
+// them in place of the gammas / binomial_attempts / slots / irv_rereads counters. Never defined in the shipped library.
+#ifdef DTB_PHASE_CLOCKS
+#define DTB_CLK_BEGIN(t) const long long t = clock64()
+#define DTB_CLK_END(t, i) do { if ((threadIdx.x & 31) == 0) stat[kStatCount + (i)] += (uint32_t)((clock64() - (t)) >> 6); } while (0)
+constexpr int kClkSlots = 8;
+#else
+#define DTB_CLK_BEGIN(t)
+#define DTB_CLK_END(t, i)
+constexpr int kClkSlots = 0;
+#endif
+
 // Where the pieces of one block's scratch live.
 template <int W>
 struct Scratch {
@@ -66,73 +79,176 @@ struct SharedFixed {
   uint8_t order[kMaxCandidates];
 };
 
-// Small items (count <= urn_max <= 8): each lane finishes whole subtrees on its own, depth-first with
-// an explicit stack of at most 8 frames (every frame holds >= 1 of the <= 8 ballots), applying the urn at
-// each node and emitting finished ballots straight into the entry list. A lane whose stack runs empty
-// claims the next item of the queue, so the warp keeps all lanes on the same loop body until the queue is
-// drained. The draws at a node depend only on (election, node), so this gives the same ballots as pushing
-// the item through the level-synchronous queue would.
+// Small items (count <= urn_max <= 8) never re-enter the level queues: a warp finishes their whole subtrees. Frames
+// (an item = an independent subtree) wait in three LIFO stacks per warp, by ballots held: 1 / 2-3 / 4-8. A pass pops up
+// to 32 frames of ONE stack, one per lane, applies the urn at each node and pushes the children (finished ballots go
+// to the entry list, one atomic per warp and emission step). Which lane takes which frame is irrelevant, so all lanes
+// stay busy until queue and stacks are empty; and because the frames of a pass hold about the same number of ballots,
+// the per-ball and per-outcome loops have the same trip count in every lane (with mixed frames the warp ran 8 rounds
+// for a mean of 1.9 balls: 8.7 of 32 lanes active). Single-ballot frames - more than half of them - take one round.
+//
+// Memory: the 1-ballot stack is this warp's slice of dynamic shared memory, the other two grow towards each other in
+// the warp's tile (the big-item path is not using it meanwhile). Neither can overflow: a frame holds >= 1 ballot (>= 2,
+// >= 4 in the other stacks), children never hold more ballots than their parent, and frames are drawn from the
+// level's queue only while the ballots held stay <= kBudget = frames per tile. The draws at a node depend only on
+// (election, node), so this gives the same ballots as pushing the item through the level-synchronous queue would.
+template <int W>
+struct WalkStacks {
+  static constexpr uint32_t kBudget = (uint32_t)(sizeof(WarpTile<W>) / sizeof(Item<W>));
+  Item<W> *light, *tile;
+  uint32_t n[3];  // warp-uniform
+  __device__ __forceinline__ Item<W> *slot(int bucket, uint32_t i) const {
+    return bucket == 0 ? light + i : bucket == 1 ? tile + i : tile + (kBudget - 1u - i);
+  }
+};
+
+__device__ __forceinline__ int walk_bucket(uint32_t count) { return count <= 1u ? 0 : count <= 3u ? 1 : 2; }
+
 template <int W, int BLOCK>
-__device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, const Item<W> *in,
-                                 uint32_t n_small, uint32_t root_depth, const RngKey key, uint32_t *stat) {
+__device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, WarpTile<W> &wt,
+                                 Item<W> *light_stack, const Item<W> *in, uint32_t n_small, uint32_t root_depth,
+                                 const RngKey key, uint32_t *stat) {
   const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t nc = a.P.nc;
-  Item<W> stack[8];
-  int top = 0;
-  bool drained = false;
+  constexpr uint32_t kBudget = WalkStacks<W>::kBudget;
+  WalkStacks<W> st;
+  st.light = light_stack;
+  st.tile = reinterpret_cast<Item<W> *>(&wt);
+  st.n[0] = st.n[1] = st.n[2] = 0;
+  uint32_t ballots = 0;             // held by the frames in the stacks (warp-uniform)
+  uint32_t pend_lo = 0, pend_hi = 0;  // queue range claimed by this warp, not yet taken in
+  bool drained = false;             // nothing left to claim
   for (;;) {
-    const bool need = top == 0 && !drained;
-    const uint32_t mask = __ballot_sync(0xffffffffu, need);
-    if (mask) {
-      const int leader = __ffs(mask) - 1;
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(&sm.next_small, (uint32_t)__popc(mask));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (need) {
-        const uint32_t idx = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-        if (idx < n_small) {
-          stack[0] = in[idx];
-          stack[0].pad_ = root_depth;
-          top = 1;
-        } else {
-          drained = true;
+    int bucket = st.n[2] >= 32u ? 2 : st.n[1] >= 32u ? 1 : st.n[0] >= 32u ? 0 : -1;
+    if (bucket < 0) {
+      // ---- take frames in from the level's queue, as many as the budget allows --------------------
+      if (pend_lo == pend_hi && !drained) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&sm.next_small, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base < n_small) {
+          pend_lo = base;
+          pend_hi = min(base + 32u, n_small);
+        }
+        drained = base + 32u >= n_small;
+      }
+      uint32_t took = 0;
+      if (pend_lo < pend_hi) {
+        const uint32_t idx = pend_lo + (uint32_t)lane;
+        Item<W> f;
+        f.count = 0;
+        if (idx < pend_hi) {
+          f = in[idx];
+          f.pad_ = root_depth;
+        }
+        uint32_t incl = f.count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const bool fits = idx < pend_hi && ballots + incl <= kBudget;
+        const uint32_t mfit = __ballot_sync(0xffffffffu, fits);
+        took = (uint32_t)__popc(mfit);
+        if (took) {
+          const int bk = walk_bucket(f.count);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const uint32_t m = __ballot_sync(0xffffffffu, fits && bk == k);
+            if (fits && bk == k) *st.slot(k, st.n[k] + (uint32_t)__popc(m & lt_mask)) = f;
+            st.n[k] += (uint32_t)__popc(m);
+          }
+          ballots += __shfl_sync(0xffffffffu, incl, (int)took - 1);
+          pend_lo += took;
+          __syncwarp();
+          continue;
         }
       }
+      // nothing could be taken in: work on what there is, heaviest first
+      bucket = st.n[2] ? 2 : st.n[1] ? 1 : st.n[0] ? 0 : -1;
+      if (bucket < 0) {
+        if (pend_lo == pend_hi && drained) break;
+        continue;  // unreachable: an empty pool always has room for a frame
+      }
     }
-    if (!__any_sync(0xffffffffu, top > 0)) break;
-    if (top == 0) continue;
-    const Item<W> f = stack[--top];
+
+    // ---- one pass over up to 32 frames of one stack ------------------------------------------------
+    const uint32_t n_before = bucket == 0 ? st.n[0] : bucket == 1 ? st.n[1] : st.n[2], take = min(n_before, 32u);
+    const bool have = (uint32_t)lane < take;
+    Item<W> f;
+    f.count = 0;
+    f.pad_ = 0;
+    if (have) f = *st.slot(bucket, n_before - 1u - (uint32_t)lane);
+    if (bucket == 0) st.n[0] -= take; else if (bucket == 1) st.n[1] -= take; else st.n[2] -= take;
+    ballots -= __reduce_add_sync(0xffffffffu, f.count);
+    __syncwarp();
+
+    // balls per outcome, 4 bits each (count <= 8, at most 33 outcomes)
+    uint64_t c0 = 0ull, c1 = 0ull, c2 = 0ull;
     const LevelInfo lv = level_info(a.P, f.pad_);
-    const uint32_t nbase = f.node >= 0 ? a.T.node_base[f.node] : 0xFFFFFFFFu;
-    stat[kStatItems] += 1;
-    stat[kStatUrnItems] += 1;
-    if (f.node >= 0) stat[kStatSlots] += lv.d;
-    const uint64_t picks = urn_picks(a, lv, f.node, nbase, f.count, key, f.node_key);
-    // balls per outcome, 4 bits each (count <= 8, at most 33 outcomes); an outcome is emitted when its first ball
-    // comes by and its counter is cleared, so every outcome is handled once without comparing balls pairwise
-    uint64_t c4[3] = {0ull, 0ull, 0ull};
-    for (uint32_t b = 0; b < f.count; ++b) {
-      const uint32_t s = (uint32_t)(picks >> (8u * b)) & 0xFFu;
-      c4[s >> 4] += 1ull << (4u * (s & 15u));
+    uint32_t nbase = 0xFFFFFFFFu;
+    if (have) {
+      if (f.node >= 0) nbase = a.T.node_base[f.node];
+      stat[kStatItems] += 1;
+      stat[kStatUrnItems] += 1;
+      if (f.node >= 0) stat[kStatSlots] += lv.d;
+#ifdef DTB_PHASE_CLOCKS
+      stat[kStatCount + (f.count == 1u ? 4 : f.count <= 3u ? 5 : 6)] += 1;
+      if (lane == 0) stat[kStatCount + 7] += 1;
+#endif
+      const uint64_t picks = urn_picks(a, lv, f.node, nbase, f.count, key, f.node_key);
+      for (uint32_t b = 0; b < f.count; ++b) {
+        const uint32_t s = (uint32_t)(picks >> (8u * b)) & 0xFFu;
+        const uint64_t inc = 1ull << (4u * (s & 15u));
+        c0 += (s >> 4) == 0u ? inc : 0ull;
+        c1 += (s >> 4) == 1u ? inc : 0ull;
+        c2 += (s >> 4) == 2u ? inc : 0ull;
+      }
     }
-    for (uint32_t b = 0; b < f.count; ++b) {
-      const uint32_t slot = (uint32_t)(picks >> (8u * b)) & 0xFFu;
-      const uint32_t c = (uint32_t)(c4[slot >> 4] >> (4u * (slot & 15u))) & 15u;
-      if (c == 0u) continue;
-      c4[slot >> 4] &= ~(15ull << (4u * (slot & 15u)));
+    // emission, one outcome per lane and step: ballots stop (entry list) or go on as a child frame
+    uint32_t pushed = 0;
+    for (;;) {
+      const bool more = (c0 | c1 | c2) != 0ull;
+      if (!__any_sync(0xffffffffu, more)) break;
+      int dest = -1;  // 0..2: child frame into that stack, 3: entry
+      uint32_t slot = 0, c = 0;
+      if (more) {
+        const int w = c0 ? 0 : c1 ? 1 : 2;
+        const uint64_t cw = w == 0 ? c0 : w == 1 ? c1 : c2;
+        const uint32_t pos = ((uint32_t)__ffsll((long long)cw) - 1u) & ~3u;
+        c = (uint32_t)(cw >> pos) & 15u;
+        const uint64_t cleared = cw & ~(15ull << pos);
+        if (w == 0) c0 = cleared; else if (w == 1) c1 = cleared; else c2 = cleared;
+        slot = 16u * (uint32_t)w + (pos >> 2);
+        dest = (slot == lv.K || lv.leaf_children) ? 3 : walk_bucket(c);  // slot K: the ballot stops here (only when lv.T)
+      }
+      const uint32_t me = __ballot_sync(0xffffffffu, dest == 3);
+      uint32_t ebase = 0;
+      if (me) {
+        if (lane == 0) ebase = atomicAdd(&sm.n_entries, (uint32_t)__popc(me));
+        ebase = __shfl_sync(0xffffffffu, ebase, 0);
+      }
+      uint32_t at = ebase + (uint32_t)__popc(me & lt_mask);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t m = __ballot_sync(0xffffffffu, dest == k);
+        if (dest == k) at = st.n[k] + (uint32_t)__popc(m & lt_mask);
+        st.n[k] += (uint32_t)__popc(m);
+      }
+      if (dest < 0) continue;
       BallotKey<W> pk = f.prefix;
       uint32_t cand = 0;
-      const bool stop = slot == lv.K;  // only possible when lv.T
+      const bool stop = slot == lv.K;
       if (!stop) {
         cand = nbase != 0xFFFFFFFFu ? (uint32_t)a.T.slot_cand[nbase + slot] : nth_unused(f.used, nc, slot);
         key_set<W>(pk, (int)lv.depth, cand);
       }
-      if (stop || lv.leaf_children) {
-        const uint32_t eo = coalesced_reserve(&sm.n_entries);
-        if (eo < a.cap_entries) {
-          sc.ent_key[eo] = pk;
-          sc.ent_cnt[eo] = c;
-          sc.ent_len[eo] = (uint8_t)(stop ? lv.depth : lv.depth + 1);
+      if (dest == 3) {
+        if (at < a.cap_entries) {
+          sc.ent_key[at] = pk;
+          sc.ent_cnt[at] = c;
+          sc.ent_len[at] = (uint8_t)(stop ? lv.depth : lv.depth + 1);
         } else {
           sm.overflow = 1;
         }
@@ -144,9 +260,12 @@ __device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<B
         ch.node = nbase != 0xFFFFFFFFu ? a.T.slot_child[nbase + slot] : -1;
         ch.used = f.used | (1u << cand);
         ch.pad_ = lv.depth + 1;
-        stack[top++] = ch;
+        *st.slot(dest, at) = ch;
+        pushed += c;
       }
     }
+    ballots += __reduce_add_sync(0xffffffffu, pushed);
+    __syncwarp();
   }
 }
 
@@ -228,11 +347,12 @@ __device__ void expand_chunk(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
 // One election's expansion. Leaves the entries in sc.ent_* and their number in sm.n_entries.
 template <int W, int BLOCK, bool LOG>
 __device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, WarpTile<W> *tiles,
-                                const RngKey key, uint32_t *stat) {
+                                Item<W> *light_stacks, const RngKey key, uint32_t *stat) {
   typedef Chunk<W> C;
   const uint32_t nc = a.P.nc;
   const int tid = threadIdx.x, lane = tid & 31;
   WarpTile<W> &wt = tiles[tid >> 5];
+  Item<W> *light_stack = light_stacks + (uint32_t)(tid >> 5) * WalkStacks<W>::kBudget;
 
   if (tid == 0) {
     sm.n_entries = 0;
@@ -274,7 +394,10 @@ __device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BL
     }
     __syncthreads();
     // Small items of this depth are walked to completion (they never re-enter a queue).
-    if (n_small) walk_small_items<W, BLOCK>(a, sc, sm, in, n_small, depth, key, stat);
+    DTB_CLK_BEGIN(t_small);
+    if (n_small) walk_small_items<W, BLOCK>(a, sc, sm, wt, light_stack, in, n_small, depth, key, stat);
+    DTB_CLK_END(t_small, 0);
+    DTB_CLK_BEGIN(t_big);
     // Big items: warps claim chunks and run the Gamma / binomial-tree path.
     int log_dp = 1;
     while ((1u << log_dp) < lv.d) ++log_dp;
@@ -288,7 +411,10 @@ __device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BL
       // big items sit at in[cap-1], in[cap-2], ...: a chunk is the ascending range ending at cap-1-start
       expand_chunk<W, BLOCK, LOG>(a, sc, sm, wt, in + (a.cap_items - start - m), m, lv, log_dp, out, key, stat);
     }
+    DTB_CLK_END(t_big, 1);
+    DTB_CLK_BEGIN(t_wait);
     __syncthreads();
+    DTB_CLK_END(t_wait, 2);
     if (tid == 0) {
       sm.n_small = lv.leaf_children ? 0u : sm.out_small;
       sm.n_big = lv.leaf_children ? 0u : sm.out_big;
@@ -302,13 +428,37 @@ __device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BL
   __syncthreads();
 }
 
+// Per-lane tallies: row c of a warp's 32 x 32 words holds what each of its lanes has added to candidate c, so adding is
+// a plain shared-memory read-modify-write without atomics or bank conflicts. flush_private_tallies sums the rows into
+// the block's tallies (lane c takes row c, starting at a different column per lane) and clears them.
+constexpr int kPrivTallyWords = 32 * kMaxCandidates;
+static_assert(kPrivTallyWords <= Chunk<1>::kTileWords, "a warp's tile doubles as its private tallies");
+
+__device__ __forceinline__ void flush_private_tallies(uint32_t *priv, uint32_t *s_tally, uint32_t nc) {
+  const uint32_t lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane < nc) {
+    uint32_t sum = 0;
+#pragma unroll 8
+    for (uint32_t j = 0; j < 32; ++j) {
+      const uint32_t col = (j + lane) & 31u;
+      sum += priv[lane * 32u + col];
+      priv[lane * 32u + col] = 0u;
+    }
+    if (sum) atomicAdd(&s_tally[lane], sum);
+  }
+  __syncwarp();
+}
+
 // socialChoiceIRV (irv_ballot.cpp:42-138) for one election. Every entry carries its current
 // holder (first standing preference); eliminating a candidate re-examines only its entries.
+// `priv` is this warp's kPrivTallyWords words of shared memory (cleared here).
 template <int W, int BLOCK>
-__device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, const RngKey key,
+__device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, uint32_t *priv, const RngKey key,
                              uint32_t n_rounds, uint32_t *stat) {
   const uint32_t nc = a.P.nc;
   const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31;
   const uint32_t n_ent = sm.n_entries;
   const uint32_t n_obs = a.n_obs;
   const BallotKey<W> *obs_key = (const BallotKey<W> *)a.obs_key;
@@ -318,22 +468,43 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
     sm.eliminated = 0;
     sm.tie_rounds = 0;
   }
+#pragma unroll 8
+  for (uint32_t j = 0; j < (uint32_t)kMaxCandidates; ++j) priv[j * 32u + lane] = 0u;
   __syncthreads();
-  // first preferences (irv_ballot.cpp:78-83); blank ballots are dropped (:55-56)
-  for (uint32_t base = 0; base < n_ent; base += BLOCK) {
-    uint32_t i = base + tid;
-    bool valid = false;
-    uint32_t cand = 0, cnt = 0;
-    if (i < n_ent) {
-      uint32_t len = sc.ent_len[i];
-      cand = len ? key_get<W>(sc.ent_key[i], 0) : 0xFFu;
-      sc.ent_holder[i] = (uint8_t)cand;
-      cnt = sc.ent_cnt[i];
-      valid = len != 0;
+  // first preferences (irv_ballot.cpp:78-83); blank ballots are dropped (:55-56). Four entries per thread and step,
+  // their loads issued together.
+  for (uint32_t base = 0; base < n_ent; base += 4u * BLOCK) {
+    uint32_t len[4], cnt[4], first[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t i = base + (uint32_t)u * BLOCK + (uint32_t)tid;
+      len[u] = 0;
+      cnt[u] = 0;
+      first[u] = 0;
+      if (i < n_ent) {
+        len[u] = sc.ent_len[i];
+        first[u] = (uint32_t)sc.ent_key[i].w[0] & 31u;
+        cnt[u] = sc.ent_cnt[i];
+      }
     }
-    warp_tally_add(sm.tally, valid, cand, cnt);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t i = base + (uint32_t)u * BLOCK + (uint32_t)tid;
+      if (i < n_ent) {
+        sc.ent_holder[i] = (uint8_t)(len[u] ? first[u] : 0xFFu);
+        if (len[u]) priv[first[u] * 32u + lane] += cnt[u];
+      }
+    }
   }
-  for (uint32_t i = tid; i < n_obs; i += BLOCK) sc.obs_holder[i] = a.obs_first[i];
+  {
+    // the observed ballots start from their first preferences, 16 holder bytes per copy
+    const uint32_t n_vec = n_obs / 16u;
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.obs_first);
+    uint4 *dst = reinterpret_cast<uint4 *>(sc.obs_holder);
+    for (uint32_t v = tid; v < n_vec; v += BLOCK) dst[v] = src[v];
+    for (uint32_t i = n_vec * 16u + (uint32_t)tid; i < n_obs; i += BLOCK) sc.obs_holder[i] = a.obs_first[i];
+  }
+  flush_private_tallies(priv, sm.tally, nc);
   __syncthreads();
 
   for (uint32_t round = 0; round < n_rounds; ++round) {
@@ -377,67 +548,72 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
     // After the last elimination nobody reads the tallies again, so the loser's ballots stay where they are
     // (the reference redistributes them, irv_ballot.cpp:109-133, without any effect on its output).
     if (round + 1u == n_rounds) continue;
-    // redistribution (irv_ballot.cpp:109-133): scan the holder bytes 16 at a time; only the entries
-    // held by the eliminated candidate are re-examined
+    // redistribution (irv_ballot.cpp:109-133): scan the holder bytes, 2 x 16 per thread and step; only the entries
+    // held by the eliminated candidate are re-examined, each lane going through its own
     const uint32_t pattern = chosen * 0x01010101u;
     for (int part = 0; part < 2; ++part) {
       uint8_t *holder = part == 0 ? sc.ent_holder : sc.obs_holder;
       const uint32_t n_part = part == 0 ? n_ent : n_obs;
       const uint32_t n_vec = (n_part + 15u) / 16u;
-      for (uint32_t vbase = 0; vbase < n_vec; vbase += BLOCK) {
-        const uint32_t v = vbase + tid;
-        uint32_t hw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (v < n_vec) {
-          const uint4 h = reinterpret_cast<const uint4 *>(holder)[v];
-          hw[0] = h.x; hw[1] = h.y; hw[2] = h.z; hw[3] = h.w;
-        }
-        // a matching byte is rare; the warp goes through its hits together
-        uint32_t hits = 0;  // bit j: byte j of this lane's 16 equals `chosen`
+      for (uint32_t vbase = 0; vbase < n_vec; vbase += 2u * BLOCK) {
+        uint4 h[2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t eq = __vcmpeq4(hw[q], pattern);  // 0xFF per equal byte
-          hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * q);
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t v = vbase + (uint32_t)u * BLOCK + (uint32_t)tid;
+          h[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+          if (v < n_vec) h[u] = reinterpret_cast<const uint4 *>(holder)[v];
         }
-        while (__any_sync(0xffffffffu, hits != 0u)) {
-          bool valid = false;
-          uint32_t cand = 0, cnt = 0;
-          if (hits) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t v = vbase + (uint32_t)u * BLOCK + (uint32_t)tid;
+          const uint32_t hw[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
+          uint32_t hits = 0;  // bit j: byte j of this lane's 16 equals `chosen`
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t eq = __vcmpeq4(hw[q], pattern);  // 0xFF per equal byte
+            hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * q);
+          }
+          while (hits) {
             const uint32_t j = (uint32_t)__ffs(hits) - 1u;
             hits &= hits - 1u;
             const uint32_t i = v * 16u + j;
-            if (i < n_part) {
-              if (part == 0) {
-                cand = first_standing<W>(sc.ent_key[i], sc.ent_len[i], eliminated);
-                cnt = sc.ent_cnt[i];
-              } else {
-                // an observed key stores at most nc-1 preferences; its length is implied by repetition
-                cand = first_standing<W>(obs_key[i], nc - 1, eliminated);
-                cnt = a.obs_cnt[i];
-              }
-              holder[i] = (uint8_t)cand;
-              valid = cand != 0xFFu;
-              stat[kStatRereads] += 1;
+            if (i >= n_part) break;
+            uint32_t cand, cnt;
+            if (part == 0) {
+              cand = first_standing<W>(sc.ent_key[i], sc.ent_len[i], eliminated);
+              cnt = sc.ent_cnt[i];
+            } else {
+              // an observed key stores at most nc-1 preferences; its length is implied by repetition
+              cand = first_standing<W>(obs_key[i], nc - 1, eliminated);
+              cnt = a.obs_cnt[i];
             }
+            holder[i] = (uint8_t)cand;
+            if (cand != 0xFFu) priv[cand * 32u + lane] += cnt;
+            stat[kStatRereads] += 1;
           }
-          warp_tally_add(sm.tally, valid, cand, cnt);
         }
       }
     }
+    flush_private_tallies(priv, sm.tally, nc);
     __syncthreads();
   }
 }
 
+#ifndef DTB_SIM_THREADS_PER_SM
+#define DTB_SIM_THREADS_PER_SM 512  // 128 registers per thread
+#endif
 template <int W, int BLOCK, bool LOG>
-__global__ void __launch_bounds__(BLOCK) simulate_kernel(const __grid_constant__ SimArgs a) {
+__global__ void __launch_bounds__(BLOCK, DTB_SIM_THREADS_PER_SM / BLOCK) simulate_kernel(const __grid_constant__ SimArgs a) {
   __shared__ SharedFixed<BLOCK> sm;
   __shared__ WarpTile<W> tiles[BLOCK / 32];
+  extern __shared__ __align__(16) uint8_t dyn_smem[];  // the walkers' single-ballot stacks (simulate_smem_bytes)
   const int tid = threadIdx.x;
   const uint32_t nc = a.P.nc;
   Scratch<W> sc;
   sc.bind(a.scratch + (uint64_t)blockIdx.x * a.scratch_stride, a.cap_items, a.cap_entries);
-  uint32_t stat[kStatCount];
+  uint32_t stat[kStatCount + kClkSlots];
 #pragma unroll
-  for (int i = 0; i < kStatCount; ++i) stat[i] = 0;
+  for (int i = 0; i < kStatCount + kClkSlots; ++i) stat[i] = 0;
   if (tid < (int)kMaxCandidates) sm.wins[tid] = 0;
 
   for (;;) {
@@ -448,7 +624,7 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const __grid_constant__
     if (e >= a.n_elections) break;
     const RngKey key = election_key(a.seed, a.first_election + e);
 
-    expand_election<W, BLOCK, LOG>(a, sc, sm, tiles, key, stat);
+    expand_election<W, BLOCK, LOG>(a, sc, sm, tiles, reinterpret_cast<Item<W> *>(dyn_smem), key, stat);
     if (tid == 0) {
       stat[kStatEntries] += sm.n_entries;
       if (a.entry_count_out) *a.entry_count_out = sm.n_entries;
@@ -458,7 +634,9 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const __grid_constant__
     // With the full order requested run nc-1 rounds (the survivor is appended); otherwise stop
     // when n_winners candidates are left (R_tree.cpp:245-253 only reads the last n_winners).
     const uint32_t n_rounds = a.elim_orders ? nc - 1 : nc - a.n_winners;
-    irv_election<W, BLOCK>(a, sc, sm, key, n_rounds, stat);
+    DTB_CLK_BEGIN(t_irv);
+    irv_election<W, BLOCK>(a, sc, sm, tiles[tid >> 5].val, key, n_rounds, stat);
+    DTB_CLK_END(t_irv, 3);
     if (tid == 0) {
       uint32_t standing = ~sm.eliminated & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
       if (a.elim_orders) {
@@ -479,6 +657,15 @@ __global__ void __launch_bounds__(BLOCK) simulate_kernel(const __grid_constant__
   __syncthreads();
   // (d) flush: one atomic per candidate per block
   if (a.run_irv && tid < (int)nc && sm.wins[tid]) atomicAdd(&a.win_counts[tid], (unsigned long long)sm.wins[tid]);
+#ifdef DTB_PHASE_CLOCKS
+  stat[kStatGammas] = stat[kStatCount + 0];
+  stat[kStatBinomials] = stat[kStatCount + 1];
+  stat[kStatSlots] = stat[kStatCount + 2];
+  stat[kStatRereads] = stat[kStatCount + 3];
+  stat[kStatEntries] = stat[kStatCount + 4];   // frames with one ballot
+  stat[kStatItems] = stat[kStatCount + 5];     // frames with 2-3 ballots
+  stat[kStatUrnItems] = stat[kStatCount + 7];  // walker passes
+#endif
   if (a.stats) {
 #pragma unroll
     for (int i = 0; i < kStatCount; ++i) {

@@ -5,9 +5,15 @@
 
 namespace dtb {
 
+// Dynamic shared memory of simulate_kernel: one stack of single-ballot frames per warp (walk_small_items).
+template <int W>
+static size_t simulate_smem_bytes(int block) {
+  return (size_t)(block / 32) * WalkStacks<W>::kBudget * sizeof(Item<W>);
+}
+
 template <int W, int BLOCK, bool LOG>
 static cudaError_t launch_one(const SimArgs &a, const LaunchCfg &cfg) {
-  size_t smem = simulate_smem_bytes(a.P.nc, BLOCK);
+  size_t smem = simulate_smem_bytes<W>(BLOCK);
   cudaError_t e = cudaFuncSetAttribute(simulate_kernel<W, BLOCK, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
@@ -33,7 +39,8 @@ cudaError_t launch_simulate(const SimArgs &a, const LaunchCfg &cfg) {
 
 template <int W, int BLOCK, bool LOG>
 static int occ_one(uint32_t nc) {
-  size_t smem = simulate_smem_bytes(nc, BLOCK);
+  (void)nc;
+  size_t smem = simulate_smem_bytes<W>(BLOCK);
   cudaFuncSetAttribute(simulate_kernel<W, BLOCK, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, simulate_kernel<W, BLOCK, LOG>, BLOCK, smem) != cudaSuccess)
@@ -56,6 +63,7 @@ int simulate_blocks_per_sm(uint32_t nc, int block, bool lg) {
 template <int W>
 __global__ void __launch_bounds__(256) irv_only_kernel(const IrvArgs ia) {
   __shared__ SharedFixed<256> sm;
+  __shared__ uint32_t priv[256 / 32][kPrivTallyWords];
   Scratch<W> sc;
   sc.bind(ia.scratch, 0, ia.cap_entries);
   SimArgs a;  // only the fields irv_election reads
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(256) irv_only_kernel(const IrvArgs ia) {
   if (threadIdx.x == 0) sm.n_entries = ia.n_entries;
   __syncthreads();
   const RngKey key = election_key(ia.seed, 0);
-  irv_election<W, 256>(a, sc, sm, key, ia.nc - 1, stat);
+  irv_election<W, 256>(a, sc, sm, priv[threadIdx.x >> 5], key, ia.nc - 1, stat);
   if (threadIdx.x == 0) {
     uint32_t standing = ~sm.eliminated & (ia.nc >= 32 ? 0xffffffffu : ((1u << ia.nc) - 1u));
     for (uint32_t r = 0; r + 1 < ia.nc; ++r) ia.order_out[r] = sm.order[r];
