@@ -194,6 +194,7 @@ struct dtree {
   uint32_t binv_max = 30;        // binomials with n p below this use inversion, the others BTRS
   uint32_t last_lane_retries = 0;  // elections lane_kernel handed to its replay in the last call read back
   uint64_t mem_avail = 0;        // device bytes the plans may use (free + held by this handle), as last queried
+  int sim_phased = -1;  // materialising path as three launches per wave: -1 when it pays off, 0 never, 1 always
   int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
   // replicas on other devices for dtree_sample_posterior_multi (owned; same parameters, tree copied when stale)
   std::vector<dtree *> replicas;
@@ -311,7 +312,8 @@ int ensure_mirror(dtree *t, cudaStream_t s) {
 struct Plan {
   int W, block, grid, blocks_per_sm;
   bool log_gamma;
-  uint32_t cap_items, cap_entries, cap_queue = 0, cap_big = 0;
+  uint32_t cap_items, cap_entries, cap_queue = 0, cap_big = 0, cap_small = 0;
+  bool phased = false;  // simulate_kernel's work as three launches per wave of `grid` elections (sim_*_kernel)
   uint32_t n_arenas = 0, arena_items = 0, arena_queue = 0, arena_big = 0;
   uint64_t arena_stride = 0, mem_budget = 0;
   uint64_t stride;        // scratch bytes per block (materialising kernel) or per warp (deferred kernel)
@@ -321,9 +323,11 @@ struct Plan {
 };
 
 template <int W>
-uint64_t scratch_bytes(uint32_t ci, uint32_t ce, uint32_t nobs) { return Scratch<W>::bytes(ci, ce, nobs); }
+uint64_t scratch_bytes(uint32_t ci, uint32_t ce, uint32_t nobs, uint32_t cs) { return Scratch<W>::bytes(ci, ce, nobs, cs); }
 
-int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, Plan &pl) {
+// Launch shape and scratch of the materialising path. allow_phased: the caller runs IRV on every election, so the job
+// may be split into the three phase kernels (dumps of a single election always take the fused kernel).
+int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, Plan &pl, bool allow_phased = false) {
   const HostParams &P = t->tree.P;
   const uint32_t nc = P.nc;
   pl.W = key_words_for(nc);
@@ -333,23 +337,29 @@ int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, P
   // there are distinct prefixes.
   uint32_t item_depth = std::min<uint32_t>(D.leaf_depth, nc - 2);          // deepest frontier
   uint32_t max_len = std::min<uint32_t>(P.max_depth ? P.max_depth : nc, nc - 1);  // longest sampled ballot
-  double items = std::min<double>((double)n_sample, falling_factorial(nc, item_depth));
+  // the level frontiers hold only items with more than urn_max ballots; the others wait in the small queue, where an
+  // item is put once (as many as there are ballots, or prefixes down to the deepest frontier)
+  double items = std::min<double>((double)(n_sample / (t->urn_max + 1) + 1), falling_factorial(nc, item_depth));
+  double smalls = 0;
+  for (uint32_t l = 0; l <= item_depth; ++l) smalls += falling_factorial(nc, l);
+  smalls = std::min<double>((double)n_sample, smalls);
+  pl.cap_small = (uint32_t)std::max(smalls, 1.0);
   double entries = 0;
   for (uint32_t l = 0; l <= max_len; ++l) entries += falling_factorial(nc, l);
   entries = std::min<double>((double)n_sample, entries);
   pl.cap_items = (uint32_t)std::max(items, 1.0);
   pl.cap_entries = (uint32_t)std::max(entries, 1.0);
   uint32_t nobs = use_obs ? t->dev.n_obs : 0;
-  pl.stride = pl.W == 1 ? scratch_bytes<1>(pl.cap_items, pl.cap_entries, nobs)
-            : pl.W == 2 ? scratch_bytes<2>(pl.cap_items, pl.cap_entries, nobs)
-                        : scratch_bytes<3>(pl.cap_items, pl.cap_entries, nobs);
+  pl.stride = pl.W == 1 ? scratch_bytes<1>(pl.cap_items, pl.cap_entries, nobs, pl.cap_small)
+            : pl.W == 2 ? scratch_bytes<2>(pl.cap_items, pl.cap_entries, nobs, pl.cap_small)
+                        : scratch_bytes<3>(pl.cap_items, pl.cap_entries, nobs, pl.cap_small);
   pl.stride = (pl.stride + 255) & ~255ull;
   pl.stride_block = pl.stride;
 
   int block = t->block_threads;
   if (block == 0) {
     // A block works on one election; size it to the widest frontier it is likely to see.
-    double work = std::min<double>(items, 1.0 + (double)t->n_nodes + (double)n_sample / 8);
+    double work = std::min<double>(smalls, 1.0 + (double)t->n_nodes + (double)n_sample / 8);
     block = work <= 48 ? 32 : work <= 512 ? 64 : work <= 8192 ? 128 : 256;
   }
   bool okb = false;
@@ -373,6 +383,16 @@ int make_plan(dtree *t, uint32_t n_sample, uint32_t n_elections, bool use_obs, P
   if (pl.stride > budget) return fail(DTREE_ERR_CUDA, "one election needs %llu bytes of scratch, more than the device has free",
                                       (unsigned long long)pl.stride);
   pl.grid = (int)grid;
+  // Three launches per wave instead of one persistent kernel once there is more than a machine-full of elections
+  // (tuning key sim_phased: -1 automatic, 0 never, 1 whenever IRV runs): a wave is up to 12 elections per SM (a whole
+  // number of rounds of resident blocks for each of the three kernels), one scratch slot each.
+  if (allow_phased && (t->sim_phased > 0 || (t->sim_phased < 0 && n_elections > 2 * grid && block == 256))) {
+    pl.phased = true;
+    const uint64_t round = 2ull * t->sm_count;
+    uint64_t wave = std::min<uint64_t>(12ull * t->sm_count, fit);
+    if (wave > round) wave -= wave % round;
+    pl.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(wave, n_elections));
+  }
   return DTREE_OK;
 }
 
@@ -444,6 +464,7 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
   a.scratch = t->d_scratch.p;
   a.scratch_stride = pl.stride;
   a.cap_items = pl.cap_items;
+  a.cap_small = pl.cap_small;
   a.cap_entries = pl.cap_entries;
   a.cap_queue = pl.cap_queue;
   a.cap_big = pl.cap_big;
@@ -456,6 +477,11 @@ cudaError_t launch(const Plan &pl, const SimArgs &a, cudaStream_t s) {
   LaunchCfg cfg{pl.block, pl.log_gamma, pl.grid, s};
   if (pl.lane) return launch_lane(a, cfg);
   if (pl.deferred) return launch_deferred(a, cfg);
+  if (pl.phased) {
+    cfg.grid = (int)a.n_elections;  // block b works on election b of the wave
+    return pl.W == 1 ? launch_simulate_phased<1>(a, cfg) : pl.W == 2 ? launch_simulate_phased<2>(a, cfg)
+                                                                   : launch_simulate_phased<3>(a, cfg);
+  }
   return pl.W == 1 ? launch_simulate<1>(a, cfg) : pl.W == 2 ? launch_simulate<2>(a, cfg) : launch_simulate<3>(a, cfg);
 }
 
@@ -638,7 +664,7 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
     if (pl.n_arenas == 0) pl.deferred = false;  // not even one worst-case arena fits: materialise instead
   }
   if (!pl.deferred) {
-    rc = make_plan(t, n_sample, n_elections, use_obs, pl);
+    rc = make_plan(t, n_sample, n_elections, use_obs, pl, true);
     if (rc) return rc;
   }
   rc = ensure_result_block(t);
@@ -815,6 +841,7 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
   j.wave = n_elections;
   if (t->should_abort) j.wave = std::min<uint64_t>(n_elections, (uint64_t)pl.grid * (pl.lane ? 1024 : pl.deferred ? 4096 : 64));
   if (pl.lane) j.wave = std::min<uint64_t>(j.wave, 1u << 20);
+  if (pl.phased) j.wave = (uint64_t)pl.grid;  // one scratch slot per election of the wave
   j.wave = std::max<uint64_t>(j.wave, 1);
   j.done = j.pilot_done = pilot_done;
   t->stats[kOutElections] = n_elections;
@@ -842,7 +869,7 @@ int job_launch_wave(Job &j) {
   CUDA_TRY(cudaMemsetAsync(&R->counter, 0, sizeof(unsigned int), j.s));
   if (j.pl.lane) CUDA_TRY(cudaMemsetAsync(t->d_retry.p, 0, sizeof(unsigned int), j.s));
   CUDA_TRY(launch(j.pl, a, j.s));
-  ++j.launches;
+  j.launches += j.pl.phased ? 3 : 1;
   if (j.pl.lane && j.replay_launch) {
     NvtxRange nv2("dtree:replay");
     SimArgs &ar = j.ar;
@@ -932,9 +959,9 @@ int run_dump(dtree *t, uint64_t election, uint32_t n_sample, const char *seed, s
   // scratch layout of block 0 (Scratch<W>::bind)
   uint8_t *base = t->d_scratch.p;
   uint8_t *p_key, *p_cnt, *p_len;
-  if (W == 1) { Scratch<1> sc; sc.bind(base, pl.cap_items, pl.cap_entries); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
-  else if (W == 2) { Scratch<2> sc; sc.bind(base, pl.cap_items, pl.cap_entries); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
-  else { Scratch<3> sc; sc.bind(base, pl.cap_items, pl.cap_entries); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+  if (W == 1) { Scratch<1> sc; sc.bind(base, pl.cap_items, pl.cap_entries, pl.cap_small); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+  else if (W == 2) { Scratch<2> sc; sc.bind(base, pl.cap_items, pl.cap_entries, pl.cap_small); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+  else { Scratch<3> sc; sc.bind(base, pl.cap_items, pl.cap_entries, pl.cap_small); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
   if (n) {
     CUDA_TRY(cudaMemcpy(keys.data(), p_key, (size_t)n * W * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(cnt.data(), p_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -1286,6 +1313,7 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
     r->tree.P = t->tree.P;
     r->host_build = t->host_build;
     r->build_mode = t->build_mode;
+    r->sim_phased = t->sim_phased;
     r->mode = t->mode;
     r->urn_max = t->urn_max;
     r->block_threads = t->block_threads;
@@ -1550,6 +1578,9 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   } else if (!strcmp(key, "lane_max_splits")) {
     if (value < -1) return fail(DTREE_ERR_ARG, "lane_max_splits must be -1 (auto), 0 (no limit) or a positive count");
     t->lane_max_splits = value;
+  } else if (!strcmp(key, "sim_phased")) {
+    if (value < -1 || value > 1) return fail(DTREE_ERR_ARG, "sim_phased must be -1 (auto), 0 or 1");
+    t->sim_phased = (int)value;
   } else if (!strcmp(key, "build_mode")) {
     if (value < 0 || value > 2) return fail(DTREE_ERR_ARG, "build_mode must be 0, 1 or 2");
     t->build_mode = (int)value;

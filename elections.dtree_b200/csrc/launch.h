@@ -19,6 +19,10 @@ constexpr int kNumBlockSizes = 4;
 // Launches simulate_kernel<W, block, log>. Returns cudaErrorInvalidValue for an unsupported block size.
 template <int W>
 cudaError_t launch_simulate(const SimArgs &a, const LaunchCfg &cfg);
+// The same elections as three launches (sim_big_kernel, sim_walk_kernel, sim_irv_kernel): cfg.grid = elections of the
+// wave, one scratch slot each.
+template <int W>
+cudaError_t launch_simulate_phased(const SimArgs &a, const LaunchCfg &cfg);
 // Resident blocks per SM for that instantiation (occupancy API).
 template <int W>
 int simulate_blocks_per_sm(uint32_t nc, int block, bool log_gamma);

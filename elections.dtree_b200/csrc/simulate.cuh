@@ -41,6 +41,8 @@ constexpr int kClkSlots = 0;
 // Where the pieces of one block's scratch live.
 template <int W>
 struct Scratch {
+  uint32_t *hdr;       // kHdr* words: what one phase kernel hands to the next (phased launches)
+  Item<W> *small;      // items with count <= urn_max, all depths: walked to completion after the level loop
   Item<W> *frontier[2];
   BallotKey<W> *ent_key;
   uint32_t *ent_cnt;
@@ -48,11 +50,15 @@ struct Scratch {
   uint8_t *ent_holder;
   uint8_t *obs_holder;
   __host__ __device__ static uint64_t align16(uint64_t x) { return (x + 15) & ~15ull; }
-  __host__ __device__ static uint64_t bytes(uint32_t cap_items, uint32_t cap_entries, uint32_t n_obs) {
-    return 2 * align16((uint64_t)cap_items * sizeof(Item<W>)) + align16((uint64_t)cap_entries * sizeof(BallotKey<W>)) +
-           align16((uint64_t)cap_entries * 4) + 2 * align16(cap_entries) + align16(n_obs);
+  __host__ __device__ static uint64_t bytes(uint32_t cap_items, uint32_t cap_entries, uint32_t n_obs,
+                                            uint32_t cap_small = 0) {
+    return 16 + align16((uint64_t)cap_small * sizeof(Item<W>)) + 2 * align16((uint64_t)cap_items * sizeof(Item<W>)) +
+           align16((uint64_t)cap_entries * sizeof(BallotKey<W>)) + align16((uint64_t)cap_entries * 4) +
+           2 * align16(cap_entries) + align16(n_obs);
   }
-  __host__ __device__ void bind(uint8_t *p, uint32_t cap_items, uint32_t cap_entries) {
+  __host__ __device__ void bind(uint8_t *p, uint32_t cap_items, uint32_t cap_entries, uint32_t cap_small = 0) {
+    hdr = (uint32_t *)p; p += 16;
+    small = (Item<W> *)p; p += align16((uint64_t)cap_small * sizeof(Item<W>));
     frontier[0] = (Item<W> *)p; p += align16((uint64_t)cap_items * sizeof(Item<W>));
     frontier[1] = (Item<W> *)p; p += align16((uint64_t)cap_items * sizeof(Item<W>));
     ent_key = (BallotKey<W> *)p; p += align16((uint64_t)cap_entries * sizeof(BallotKey<W>));
@@ -63,12 +69,14 @@ struct Scratch {
   }
 };
 
+enum { kHdrSmall = 0, kHdrEntries, kHdrOverflow, kHdrWords = 4 };
+
 template <int BLOCK>
 struct SharedFixed {
   // frontier bookkeeping of the level being processed / produced
-  uint32_t n_small, n_big;        // items at the front (small counts) / back (Gamma path) of the input queue
+  uint32_t n_big;                 // items of the input frontier (all with count > urn_max: the Gamma path)
   uint32_t next_small, next_big;  // chunk cursors
-  uint32_t out_small, out_big;    // items appended to the output queue
+  uint32_t out_small, out_big;    // items appended to the small queue (never reset) / the output frontier
   uint32_t n_entries;
   uint32_t overflow;
   // IRV
@@ -92,29 +100,36 @@ struct SharedFixed {
 // >= 4 in the other stacks), children never hold more ballots than their parent, and frames are drawn from the
 // level's queue only while the ballots held stay <= kBudget = frames per tile. The draws at a node depend only on
 // (election, node), so this gives the same ballots as pushing the item through the level-synchronous queue would.
-template <int W>
+template <int W, uint32_t B>
 struct WalkStacks {
-  static constexpr uint32_t kBudget = (uint32_t)(sizeof(WarpTile<W>) / sizeof(Item<W>));
-  Item<W> *light, *tile;
-  uint32_t n[3];  // warp-uniform
+  Item<W> *light, *tile;  // B frames (1 ballot each), B / 2 frames (2-3 ballots from the front, 4-8 from the back)
+  uint32_t n[3];          // warp-uniform
   __device__ __forceinline__ Item<W> *slot(int bucket, uint32_t i) const {
-    return bucket == 0 ? light + i : bucket == 1 ? tile + i : tile + (kBudget - 1u - i);
+    return bucket == 0 ? light + i : bucket == 1 ? tile + i : tile + (B / 2u - 1u - i);
   }
+};
+// Ballot budget of a warp's stacks. In simulate_kernel the 2-3 / 4-8 stacks live in the warp's tile and the single-ballot
+// stack in dynamic shared memory; the phase kernel sim_walk_kernel has both in dynamic shared memory and a smaller budget,
+// so that four blocks fit an SM.
+template <int W>
+struct WalkBudget {
+  static constexpr uint32_t kFused = (uint32_t)(sizeof(WarpTile<W>) / sizeof(Item<W>)) & ~1u;
+  static constexpr uint32_t kPhased = W == 1 ? 128 : 80;  // 32 warps x 1.5 x kPhased frames within 227 KB
 };
 
 __device__ __forceinline__ int walk_bucket(uint32_t count) { return count <= 1u ? 0 : count <= 3u ? 1 : 2; }
 
-template <int W, int BLOCK>
-__device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, WarpTile<W> &wt,
-                                 Item<W> *light_stack, const Item<W> *in, uint32_t n_small, uint32_t root_depth,
-                                 const RngKey key, uint32_t *stat) {
+template <int W, int BLOCK, uint32_t B>
+__device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, Item<W> *tile_stack,
+                                 Item<W> *light_stack, const Item<W> *in, uint32_t n_small, const RngKey key,
+                                 uint32_t *stat) {
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t nc = a.P.nc;
-  constexpr uint32_t kBudget = WalkStacks<W>::kBudget;
-  WalkStacks<W> st;
+  constexpr uint32_t kBudget = B;
+  WalkStacks<W, B> st;
   st.light = light_stack;
-  st.tile = reinterpret_cast<Item<W> *>(&wt);
+  st.tile = tile_stack;
   st.n[0] = st.n[1] = st.n[2] = 0;
   uint32_t ballots = 0;             // held by the frames in the stacks (warp-uniform)
   uint32_t pend_lo = 0, pend_hi = 0;  // queue range claimed by this warp, not yet taken in
@@ -138,17 +153,21 @@ __device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<B
         const uint32_t idx = pend_lo + (uint32_t)lane;
         Item<W> f;
         f.count = 0;
-        if (idx < pend_hi) {
-          f = in[idx];
-          f.pad_ = root_depth;
-        }
-        uint32_t incl = f.count;
+        if (idx < pend_hi) f = in[idx];
+        // usually all of them fit; otherwise the longest prefix that does
+        const uint32_t all = __reduce_add_sync(0xffffffffu, f.count);
+        bool fits = idx < pend_hi;
+        uint32_t taken = all;
+        if (ballots + all > kBudget) {
+          uint32_t incl = f.count;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += up;
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+          }
+          fits = fits && ballots + incl <= kBudget;
+          taken = __reduce_add_sync(0xffffffffu, fits ? f.count : 0u);
         }
-        const bool fits = idx < pend_hi && ballots + incl <= kBudget;
         const uint32_t mfit = __ballot_sync(0xffffffffu, fits);
         took = (uint32_t)__popc(mfit);
         if (took) {
@@ -159,7 +178,7 @@ __device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<B
             if (fits && bk == k) *st.slot(k, st.n[k] + (uint32_t)__popc(m & lt_mask)) = f;
             st.n[k] += (uint32_t)__popc(m);
           }
-          ballots += __shfl_sync(0xffffffffu, incl, (int)took - 1);
+          ballots += taken;
           pend_lo += took;
           __syncwarp();
           continue;
@@ -198,12 +217,16 @@ __device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<B
       if (lane == 0) stat[kStatCount + 7] += 1;
 #endif
       const uint64_t picks = urn_picks(a, lv, f.node, nbase, f.count, key, f.node_key);
-      for (uint32_t b = 0; b < f.count; ++b) {
-        const uint32_t s = (uint32_t)(picks >> (8u * b)) & 0xFFu;
-        const uint64_t inc = 1ull << (4u * (s & 15u));
-        c0 += (s >> 4) == 0u ? inc : 0ull;
-        c1 += (s >> 4) == 1u ? inc : 0ull;
-        c2 += (s >> 4) == 2u ? inc : 0ull;
+      if (nc < 16u) {  // at most 16 outcomes anywhere in the tree: one word of nibbles
+        for (uint32_t b = 0; b < f.count; ++b) c0 += 1ull << (4u * ((uint32_t)(picks >> (8u * b)) & 15u));
+      } else {
+        for (uint32_t b = 0; b < f.count; ++b) {
+          const uint32_t s = (uint32_t)(picks >> (8u * b)) & 0xFFu;
+          const uint64_t inc = 1ull << (4u * (s & 15u));
+          c0 += (s >> 4) == 0u ? inc : 0ull;
+          c1 += (s >> 4) == 1u ? inc : 0ull;
+          c2 += (s >> 4) == 2u ? inc : 0ull;
+        }
       }
     }
     // emission, one outcome per lane and step: ballots stop (entry list) or go on as a child frame
@@ -330,34 +353,33 @@ __device__ void expand_chunk(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
       ch.node = nb != 0xFFFFFFFFu ? a.T.slot_child[nb + slot] : -1;
       ch.used = par.used | (1u << cand);
       ch.pad_ = lv.depth + 1;
-      // two-ended queue: small items from the front, big items from the back; they must not meet.
-      // Both cursors already include this lane's reservation, so the test is conservative.
-      if (sm.out_small + sm.out_big > a.cap_items) {
-        sm.overflow = 1;
-      } else if (dest == 2) {
-        out[so] = ch;
+      // small counts wait in the election's small queue (walked after the level loop), the others form the next frontier
+      if (dest == 2) {
+        if (so < a.cap_small) sc.small[so] = ch;
+        else sm.overflow = 1;
       } else {
-        out[a.cap_items - 1u - bo] = ch;
+        if (bo < a.cap_items) out[bo] = ch;
+        else sm.overflow = 1;
       }
     }
   }
   __syncwarp();
 }
 
-// One election's expansion. Leaves the entries in sc.ent_* and their number in sm.n_entries.
+// The level loop of one election: items with count > urn_max, level-synchronously. Leaves their finished ballots in
+// sc.ent_* (sm.n_entries) and every child with count <= urn_max in sc.small (sm.out_small).
 template <int W, int BLOCK, bool LOG>
-__device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, WarpTile<W> *tiles,
-                                Item<W> *light_stacks, const RngKey key, uint32_t *stat) {
+__device__ void expand_big_levels(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, WarpTile<W> *tiles,
+                                  const RngKey key, uint32_t *stat) {
   typedef Chunk<W> C;
   const uint32_t nc = a.P.nc;
   const int tid = threadIdx.x, lane = tid & 31;
   WarpTile<W> &wt = tiles[tid >> 5];
-  Item<W> *light_stack = light_stacks + (uint32_t)(tid >> 5) * WalkStacks<W>::kBudget;
 
   if (tid == 0) {
     sm.n_entries = 0;
     sm.overflow = 0;
-    sm.n_small = 0;
+    sm.out_small = 0;
     sm.n_big = 0;
     if (a.n_sample > 0) {
       Item<W> root;
@@ -369,10 +391,10 @@ __device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BL
       root.used = 0;
       root.pad_ = 0;
       if (a.n_sample <= a.urn_max) {
-        sc.frontier[0][0] = root;
-        sm.n_small = 1;
+        sc.small[0] = root;
+        sm.out_small = 1;
       } else {
-        sc.frontier[0][a.cap_items - 1] = root;
+        sc.frontier[0][0] = root;
         sm.n_big = 1;
       }
     }
@@ -381,50 +403,58 @@ __device__ void expand_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BL
 
   int cur = 0;
   for (uint32_t depth = 0; depth + 1 < nc; ++depth) {
-    const uint32_t n_small = sm.n_small, n_big = sm.n_big;
-    if (n_small + n_big == 0) break;
+    const uint32_t n_big = sm.n_big;
+    if (n_big == 0) break;
     const LevelInfo lv = level_info(a.P, depth);
     const Item<W> *in = sc.frontier[cur];
     Item<W> *out = sc.frontier[cur ^ 1];
     if (tid == 0) {
-      sm.next_small = 0;
       sm.next_big = 0;
-      sm.out_small = 0;
       sm.out_big = 0;
     }
     __syncthreads();
-    // Small items of this depth are walked to completion (they never re-enter a queue).
-    DTB_CLK_BEGIN(t_small);
-    if (n_small) walk_small_items<W, BLOCK>(a, sc, sm, wt, light_stack, in, n_small, depth, key, stat);
-    DTB_CLK_END(t_small, 0);
-    DTB_CLK_BEGIN(t_big);
-    // Big items: warps claim chunks and run the Gamma / binomial-tree path.
+    // warps claim chunks and run the Gamma / binomial-tree path
     int log_dp = 1;
     while ((1u << log_dp) < lv.d) ++log_dp;
     const uint32_t ci = min((uint32_t)C::kMaxItems, (uint32_t)C::kTileWords / (2u * (1u << log_dp) + 1u));
+    DTB_CLK_BEGIN(t_big);
     for (;;) {
       uint32_t start = 0;
       if (lane == 0) start = atomicAdd(&sm.next_big, ci);
       start = __shfl_sync(0xffffffffu, start, 0);
       if (start >= n_big) break;
       const uint32_t m = min(ci, n_big - start);
-      // big items sit at in[cap-1], in[cap-2], ...: a chunk is the ascending range ending at cap-1-start
-      expand_chunk<W, BLOCK, LOG>(a, sc, sm, wt, in + (a.cap_items - start - m), m, lv, log_dp, out, key, stat);
+      expand_chunk<W, BLOCK, LOG>(a, sc, sm, wt, in + start, m, lv, log_dp, out, key, stat);
     }
     DTB_CLK_END(t_big, 1);
     DTB_CLK_BEGIN(t_wait);
     __syncthreads();
     DTB_CLK_END(t_wait, 2);
-    if (tid == 0) {
-      sm.n_small = lv.leaf_children ? 0u : sm.out_small;
-      sm.n_big = lv.leaf_children ? 0u : sm.out_big;
-      if (sm.overflow) *a.error_flag = 1;
-    }
+    if (tid == 0) sm.n_big = lv.leaf_children ? 0u : min(sm.out_big, a.cap_items);
     cur ^= 1;
     __syncthreads();
     if (sm.overflow) break;
   }
-  if (tid == 0 && sm.n_entries > a.cap_entries) sm.n_entries = a.cap_entries;
+  __syncthreads();
+}
+
+// The small queue of one election, walked to completion by all warps of the block. tile_stacks / light_stacks: B / 2
+// and B frames of shared memory per warp.
+template <int W, int BLOCK, uint32_t B>
+__device__ void walk_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK> &sm, Item<W> *tile_stack,
+                              Item<W> *light_stack, const RngKey key, uint32_t *stat) {
+  const int tid = threadIdx.x;
+  if (tid == 0) sm.next_small = 0;
+  __syncthreads();
+  const uint32_t n_small = min(sm.out_small, a.cap_small);
+  DTB_CLK_BEGIN(t_small);
+  if (n_small) walk_small_items<W, BLOCK, B>(a, sc, sm, tile_stack, light_stack, sc.small, n_small, key, stat);
+  DTB_CLK_END(t_small, 0);
+  __syncthreads();
+  if (tid == 0) {
+    if (sm.n_entries > a.cap_entries) sm.n_entries = a.cap_entries;
+    if (sm.overflow) *a.error_flag = 1;
+  }
   __syncthreads();
 }
 
@@ -599,64 +629,28 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
   }
 }
 
-#ifndef DTB_SIM_THREADS_PER_SM
-#define DTB_SIM_THREADS_PER_SM 512  // 128 registers per thread
-#endif
-template <int W, int BLOCK, bool LOG>
-__global__ void __launch_bounds__(BLOCK, DTB_SIM_THREADS_PER_SM / BLOCK) simulate_kernel(const __grid_constant__ SimArgs a) {
-  __shared__ SharedFixed<BLOCK> sm;
-  __shared__ WarpTile<W> tiles[BLOCK / 32];
-  extern __shared__ __align__(16) uint8_t dyn_smem[];  // the walkers' single-ballot stacks (simulate_smem_bytes)
-  const int tid = threadIdx.x;
+// Thread 0, after irv_election: the election's order / winners (R_tree.cpp:245-253 reads the last n_winners).
+template <int BLOCK>
+__device__ __forceinline__ void record_outcome(const SimArgs &a, SharedFixed<BLOCK> &sm, uint32_t e) {
   const uint32_t nc = a.P.nc;
-  Scratch<W> sc;
-  sc.bind(a.scratch + (uint64_t)blockIdx.x * a.scratch_stride, a.cap_items, a.cap_entries);
-  uint32_t stat[kStatCount + kClkSlots];
-#pragma unroll
-  for (int i = 0; i < kStatCount + kClkSlots; ++i) stat[i] = 0;
-  if (tid < (int)kMaxCandidates) sm.wins[tid] = 0;
-
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) sm.election = atomicAdd(a.work_counter, 1u);
-    __syncthreads();
-    const uint32_t e = sm.election;
-    if (e >= a.n_elections) break;
-    const RngKey key = election_key(a.seed, a.first_election + e);
-
-    expand_election<W, BLOCK, LOG>(a, sc, sm, tiles, reinterpret_cast<Item<W> *>(dyn_smem), key, stat);
-    if (tid == 0) {
-      stat[kStatEntries] += sm.n_entries;
-      if (a.entry_count_out) *a.entry_count_out = sm.n_entries;
-    }
-    if (!a.run_irv) continue;
-
-    // With the full order requested run nc-1 rounds (the survivor is appended); otherwise stop
-    // when n_winners candidates are left (R_tree.cpp:245-253 only reads the last n_winners).
-    const uint32_t n_rounds = a.elim_orders ? nc - 1 : nc - a.n_winners;
-    DTB_CLK_BEGIN(t_irv);
-    irv_election<W, BLOCK>(a, sc, sm, tiles[tid >> 5].val, key, n_rounds, stat);
-    DTB_CLK_END(t_irv, 3);
-    if (tid == 0) {
-      uint32_t standing = ~sm.eliminated & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
-      if (a.elim_orders) {
-        uint8_t *o = a.elim_orders + (uint64_t)e * nc;
-        for (uint32_t r = 0; r + 1 < nc; ++r) o[r] = sm.order[r];
-        o[nc - 1] = (uint8_t)(__ffs(standing) - 1);
-        // winners = last n_winners of the order
-        for (uint32_t r = nc - a.n_winners; r < nc; ++r) sm.wins[o[r]] += 1;
-      } else {
-        while (standing) {
-          sm.wins[__ffs(standing) - 1] += 1;
-          standing &= standing - 1u;
-        }
-      }
-      if (a.tie_rounds_out) a.tie_rounds_out[e] = sm.tie_rounds;
+  uint32_t standing = ~sm.eliminated & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+  if (a.elim_orders) {
+    uint8_t *o = a.elim_orders + (uint64_t)e * nc;
+    for (uint32_t r = 0; r + 1 < nc; ++r) o[r] = sm.order[r];
+    o[nc - 1] = (uint8_t)(__ffs(standing) - 1);
+    // winners = last n_winners of the order
+    for (uint32_t r = nc - a.n_winners; r < nc; ++r) sm.wins[o[r]] += 1;
+  } else {
+    while (standing) {
+      sm.wins[__ffs(standing) - 1] += 1;
+      standing &= standing - 1u;
     }
   }
-  __syncthreads();
-  // (d) flush: one atomic per candidate per block
-  if (a.run_irv && tid < (int)nc && sm.wins[tid]) atomicAdd(&a.win_counts[tid], (unsigned long long)sm.wins[tid]);
+  if (a.tie_rounds_out) a.tie_rounds_out[e] = sm.tie_rounds;
+}
+
+// Per-thread counters into the call's statistics, one atomic per warp and counter.
+__device__ __forceinline__ void flush_stats(const SimArgs &a, uint32_t *stat) {
 #ifdef DTB_PHASE_CLOCKS
   stat[kStatGammas] = stat[kStatCount + 0];
   stat[kStatBinomials] = stat[kStatCount + 1];
@@ -670,9 +664,142 @@ __global__ void __launch_bounds__(BLOCK, DTB_SIM_THREADS_PER_SM / BLOCK) simulat
 #pragma unroll
     for (int i = 0; i < kStatCount; ++i) {
       uint32_t s = __reduce_add_sync(0xffffffffu, stat[i]);
-      if ((tid & 31) == 0 && s) atomicAdd(&a.stats[i], (unsigned long long)s);
+      if ((threadIdx.x & 31) == 0 && s) atomicAdd(&a.stats[i], (unsigned long long)s);
     }
   }
+}
+
+#ifndef DTB_SIM_THREADS_PER_SM
+#define DTB_SIM_THREADS_PER_SM 512  // 128 registers per thread
+#endif
+template <int W, int BLOCK, bool LOG>
+__global__ void __launch_bounds__(BLOCK, DTB_SIM_THREADS_PER_SM / BLOCK) simulate_kernel(const __grid_constant__ SimArgs a) {
+  __shared__ SharedFixed<BLOCK> sm;
+  __shared__ WarpTile<W> tiles[BLOCK / 32];
+  extern __shared__ __align__(16) uint8_t dyn_smem[];  // the walkers' single-ballot stacks (simulate_smem_bytes)
+  const int tid = threadIdx.x;
+  const uint32_t nc = a.P.nc;
+  Scratch<W> sc;
+  sc.bind(a.scratch + (uint64_t)blockIdx.x * a.scratch_stride, a.cap_items, a.cap_entries, a.cap_small);
+  uint32_t stat[kStatCount + kClkSlots];
+#pragma unroll
+  for (int i = 0; i < kStatCount + kClkSlots; ++i) stat[i] = 0;
+  if (tid < (int)kMaxCandidates) sm.wins[tid] = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sm.election = atomicAdd(a.work_counter, 1u);
+    __syncthreads();
+    const uint32_t e = sm.election;
+    if (e >= a.n_elections) break;
+    const RngKey key = election_key(a.seed, a.first_election + e);
+
+    expand_big_levels<W, BLOCK, LOG>(a, sc, sm, tiles, key, stat);
+    walk_election<W, BLOCK, WalkBudget<W>::kFused>(
+        a, sc, sm, reinterpret_cast<Item<W> *>(&tiles[tid >> 5]),
+        reinterpret_cast<Item<W> *>(dyn_smem) + (uint32_t)(tid >> 5) * WalkBudget<W>::kFused, key, stat);
+    if (tid == 0) {
+      stat[kStatEntries] += sm.n_entries;
+      if (a.entry_count_out) *a.entry_count_out = sm.n_entries;
+    }
+    if (!a.run_irv) continue;
+
+    // With the full order requested run nc-1 rounds (the survivor is appended); otherwise stop
+    // when n_winners candidates are left (R_tree.cpp:245-253 only reads the last n_winners).
+    const uint32_t n_rounds = a.elim_orders ? nc - 1 : nc - a.n_winners;
+    DTB_CLK_BEGIN(t_irv);
+    irv_election<W, BLOCK>(a, sc, sm, tiles[tid >> 5].val, key, n_rounds, stat);
+    DTB_CLK_END(t_irv, 3);
+    if (tid == 0) record_outcome<BLOCK>(a, sm, e);
+  }
+  __syncthreads();
+  // (d) flush: one atomic per candidate per block
+  if (a.run_irv && tid < (int)nc && sm.wins[tid]) atomicAdd(&a.win_counts[tid], (unsigned long long)sm.wins[tid]);
+  flush_stats(a, stat);
+}
+
+// ---- the same election in three launches ---------------------------------------------------------------------------
+// The level loop needs 128 registers per thread (Marsaglia-Tsang, BTRS), the walkers and the IRV stage far fewer, and
+// all three spend most of their time waiting on dependent loads and dependent arithmetic: halving the resident warps
+// more than halves the rate. As separate kernels over a wave of elections - block b works on election b of the wave in
+// scratch slot b, the header words of the slot carrying the counts from one launch to the next - the walkers and the IRV
+// stage run with two to three times the warps per SM. Same device functions, same draws, same outcomes.
+template <int W, int BLOCK, bool LOG>
+__global__ void __launch_bounds__(BLOCK, DTB_SIM_THREADS_PER_SM / BLOCK) sim_big_kernel(const __grid_constant__ SimArgs a) {
+  __shared__ SharedFixed<BLOCK> sm;
+  __shared__ WarpTile<W> tiles[BLOCK / 32];
+  const int tid = threadIdx.x;
+  const uint32_t e = blockIdx.x;
+  Scratch<W> sc;
+  sc.bind(a.scratch + (uint64_t)e * a.scratch_stride, a.cap_items, a.cap_entries, a.cap_small);
+  uint32_t stat[kStatCount + kClkSlots];
+#pragma unroll
+  for (int i = 0; i < kStatCount + kClkSlots; ++i) stat[i] = 0;
+  expand_big_levels<W, BLOCK, LOG>(a, sc, sm, tiles, election_key(a.seed, a.first_election + e), stat);
+  if (tid == 0) {
+    sc.hdr[kHdrSmall] = sm.out_small;
+    sc.hdr[kHdrEntries] = sm.n_entries;
+    sc.hdr[kHdrOverflow] = sm.overflow;
+    if (sm.overflow) *a.error_flag = 1;
+  }
+  flush_stats(a, stat);
+}
+
+#ifndef DTB_WALK_THREADS_PER_SM
+#define DTB_WALK_THREADS_PER_SM 1024
+#endif
+template <int W, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, DTB_WALK_THREADS_PER_SM / BLOCK) sim_walk_kernel(const __grid_constant__ SimArgs a) {
+  __shared__ SharedFixed<BLOCK> sm;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];  // per warp: kPhased + kPhased / 2 frames
+  constexpr uint32_t B = WalkBudget<W>::kPhased;
+  const int tid = threadIdx.x;
+  const uint32_t e = blockIdx.x;
+  Scratch<W> sc;
+  sc.bind(a.scratch + (uint64_t)e * a.scratch_stride, a.cap_items, a.cap_entries, a.cap_small);
+  uint32_t stat[kStatCount + kClkSlots];
+#pragma unroll
+  for (int i = 0; i < kStatCount + kClkSlots; ++i) stat[i] = 0;
+  if (tid == 0) {
+    sm.out_small = sc.hdr[kHdrSmall];
+    sm.n_entries = sc.hdr[kHdrEntries];
+    sm.overflow = sc.hdr[kHdrOverflow];
+  }
+  __syncthreads();
+  Item<W> *mine = reinterpret_cast<Item<W> *>(dyn_smem) + (uint32_t)(tid >> 5) * (B + B / 2u);
+  walk_election<W, BLOCK, B>(a, sc, sm, mine + B, mine, election_key(a.seed, a.first_election + e), stat);
+  if (tid == 0) {
+    sc.hdr[kHdrEntries] = sm.n_entries;
+    stat[kStatEntries] += sm.n_entries;
+  }
+  flush_stats(a, stat);
+}
+
+#ifndef DTB_IRV_THREADS_PER_SM
+#define DTB_IRV_THREADS_PER_SM 1536
+#endif
+template <int W, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, DTB_IRV_THREADS_PER_SM / BLOCK) sim_irv_kernel(const __grid_constant__ SimArgs a) {
+  __shared__ SharedFixed<BLOCK> sm;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];  // kPrivTallyWords words per warp
+  uint32_t *priv = reinterpret_cast<uint32_t *>(dyn_smem) + (uint32_t)(threadIdx.x >> 5) * kPrivTallyWords;
+  const int tid = threadIdx.x;
+  const uint32_t nc = a.P.nc;
+  const uint32_t e = blockIdx.x;
+  Scratch<W> sc;
+  sc.bind(a.scratch + (uint64_t)e * a.scratch_stride, a.cap_items, a.cap_entries, a.cap_small);
+  uint32_t stat[kStatCount + kClkSlots];
+#pragma unroll
+  for (int i = 0; i < kStatCount + kClkSlots; ++i) stat[i] = 0;
+  if (tid < (int)kMaxCandidates) sm.wins[tid] = 0;
+  if (tid == 0) sm.n_entries = sc.hdr[kHdrEntries];
+  __syncthreads();
+  const uint32_t n_rounds = a.elim_orders ? nc - 1 : nc - a.n_winners;
+  irv_election<W, BLOCK>(a, sc, sm, priv, election_key(a.seed, a.first_election + e), n_rounds, stat);
+  if (tid == 0) record_outcome<BLOCK>(a, sm, e);
+  __syncthreads();
+  if (tid < (int)nc && sm.wins[tid]) atomicAdd(&a.win_counts[tid], (unsigned long long)sm.wins[tid]);
+  flush_stats(a, stat);
 }
 
 }  // namespace dtb

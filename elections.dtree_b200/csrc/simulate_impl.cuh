@@ -8,7 +8,51 @@ namespace dtb {
 // Dynamic shared memory of simulate_kernel: one stack of single-ballot frames per warp (walk_small_items).
 template <int W>
 static size_t simulate_smem_bytes(int block) {
-  return (size_t)(block / 32) * WalkStacks<W>::kBudget * sizeof(Item<W>);
+  return (size_t)(block / 32) * WalkBudget<W>::kFused * sizeof(Item<W>);
+}
+
+// The three phase kernels over a wave of cfg.grid elections, block b on election b in scratch slot b. The walkers and
+// the IRV stage run with large blocks (an election is finished sooner, so the tail of a wave is shorter).
+#ifndef DTB_WALK_BLOCK
+#define DTB_WALK_BLOCK 1024
+#endif
+#ifndef DTB_IRV_BLOCK
+#define DTB_IRV_BLOCK 768
+#endif
+constexpr int kWalkBlock = DTB_WALK_BLOCK, kIrvBlock = DTB_IRV_BLOCK;
+template <int W>
+static size_t walk_smem_bytes() {
+  return (size_t)(kWalkBlock / 32) * (WalkBudget<W>::kPhased + WalkBudget<W>::kPhased / 2) * sizeof(Item<W>);
+}
+
+template <int W, int BLOCK, bool LOG>
+static cudaError_t launch_phased_one(const SimArgs &a, const LaunchCfg &cfg) {
+  const size_t wsm = walk_smem_bytes<W>();
+  cudaError_t e = cudaFuncSetAttribute(sim_walk_kernel<W, kWalkBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
+  if (e != cudaSuccess) return e;
+  const size_t ism = (size_t)(kIrvBlock / 32) * kPrivTallyWords * sizeof(uint32_t);
+  e = cudaFuncSetAttribute(sim_irv_kernel<W, kIrvBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism);
+  if (e != cudaSuccess) return e;
+  sim_big_kernel<W, BLOCK, LOG><<<cfg.grid, BLOCK, 0, cfg.stream>>>(a);
+  sim_walk_kernel<W, kWalkBlock><<<cfg.grid, kWalkBlock, wsm, cfg.stream>>>(a);
+  sim_irv_kernel<W, kIrvBlock><<<cfg.grid, kIrvBlock, ism, cfg.stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int W, bool LOG>
+static cudaError_t launch_phased_block(const SimArgs &a, const LaunchCfg &cfg) {
+  switch (cfg.block) {
+    case 32: return launch_phased_one<W, 32, LOG>(a, cfg);
+    case 64: return launch_phased_one<W, 64, LOG>(a, cfg);
+    case 128: return launch_phased_one<W, 128, LOG>(a, cfg);
+    case 256: return launch_phased_one<W, 256, LOG>(a, cfg);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int W>
+cudaError_t launch_simulate_phased(const SimArgs &a, const LaunchCfg &cfg) {
+  return cfg.log_gamma ? launch_phased_block<W, true>(a, cfg) : launch_phased_block<W, false>(a, cfg);
 }
 
 template <int W, int BLOCK, bool LOG>
@@ -98,6 +142,7 @@ cudaError_t launch_irv_only(const IrvArgs &a, cudaStream_t stream) {
 
 #define DTREE_INSTANTIATE(W)                                                          \
   template cudaError_t launch_simulate<W>(const SimArgs &, const LaunchCfg &);        \
+  template cudaError_t launch_simulate_phased<W>(const SimArgs &, const LaunchCfg &); \
   template int simulate_blocks_per_sm<W>(uint32_t, int, bool);                        \
   template cudaError_t launch_irv_only<W>(const IrvArgs &, cudaStream_t);
 

@@ -51,6 +51,7 @@ struct SimArgs {
   uint8_t *scratch;
   uint64_t scratch_stride;    // bytes per block
   uint32_t cap_items;         // frontier capacity (items) per buffer
+  uint32_t cap_small;         // simulate_kernel: capacity of an election's small-item queue
   uint32_t cap_entries;
   uint32_t cap_queue, cap_big; // deferred kernel: circular work queue / big-count lists (items)
   // deferred kernel: a few worst-case arenas for the elections that outgrow their warp's scratch

@@ -290,16 +290,20 @@ def test_deferred_equals_materialised(pkg, L, nc, mn, mx, a0, vd, n_obs, n_ballo
             warnings.simplefilter("ignore")
             t.update_indices(prefs, offsets)
     res = {}
-    for mode in (0, 1, 2):
-        t.tune(mode=mode)
+    # "0p": the materialising path as three launches per wave (sim_big / sim_walk / sim_irv kernels) instead of one
+    for mode in (0, "0p", 1, 2):
+        t.tune(mode=0 if mode == "0p" else mode, sim_phased=1 if mode == "0p" else 0)
         out = []
         for nw in ((1, 2) if nc > 2 else (1,)):
             out.append(t.sample_posterior_counts(400, n_ballots, n_winners=nw, replace=replace, seed="DEFER",
                                                  return_orders=True))
             out.append((t.sample_posterior_counts(400, n_ballots, n_winners=nw, replace=replace, seed="DEFER"), None))
-        assert t.last_stats()["mode"] == mode
+        st = t.last_stats()
+        assert st["mode"] == (0 if mode == "0p" else mode)
+        if mode in (0, "0p"):
+            assert st["launches"] == (3 if mode == "0p" else 1)
         res[mode] = out
-    for mode in (1, 2):
+    for mode in ("0p", 1, 2):
         for a, b in zip(res[0], res[mode]):
             assert a[0].tolist() == b[0].tolist(), mode
             assert (a[1] is None and b[1] is None) or np.array_equal(a[1], b[1]), mode

@@ -28,7 +28,7 @@ for rep in range(3):
     best = dt if best is None else min(best, dt)
 st = t.last_stats()
 clk = "clk" in os.environ.get("DTREE_B200_LIB", "")
-out = {"scratch_GB": round(st["scratch_bytes"] / 1e9, 2), "case": case, "elections": n, "ms": round(best * 1e3, 2), "elections_per_s": round(n / best), "wins": w.tolist()}
+out = {"launches": st["launches"], "scratch_GB": round(st["scratch_bytes"] / 1e9, 2), "case": case, "elections": n, "ms": round(best * 1e3, 2), "elections_per_s": round(n / best), "wins": w.tolist()}
 if clk:
     warps = 296 * 8
     tot = best * 1.965e9  # cycles of the whole call at 1965 MHz
