@@ -229,10 +229,16 @@ __device__ __forceinline__ uint32_t binv(uint32_t n, float ps, uint32_t bits) {
   float u = u01f(bits);
   uint32_t k = 0;
   const uint32_t kmax = n < 192u ? n : 192u;
+  // P(k) = P(k-1) t_k, t_k = (n+1)/k p/q - p/q. t_{k+1} is formed while step k is being decided (it depends on k
+  // alone), which leaves one multiplication and one subtraction on the loop-carried path; k is carried as a float
+  // (exact). Same operations on the same values as the plain loop: the same k for the same uniform.
+  float kf = 1.0f, t = __fadd_rn(__fdividef(a, 1.0f), -s);
   while (u > pk && k < kmax) {
     u = __fadd_rn(u, -pk);
     ++k;
-    pk = __fmul_rn(pk, __fadd_rn(__fdividef(a, (float)k), -s));  // P(k) = P(k-1) ((n+1)/k - 1) p/q
+    pk = __fmul_rn(pk, t);
+    kf = __fadd_rn(kf, 1.0f);
+    t = __fadd_rn(__fdividef(a, kf), -s);
   }
   return k;
 }
