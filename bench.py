@@ -19,6 +19,8 @@ about `--step-ms` (a single C3 job is ~1 ms, far too short to time robustly), id
  workloads  (N = 1) the other BASELINE configurations and a close-race C3 shape, each with the kernel the library
             chose, node splits per election and its roofline on its own and on SURVEY 8(d)'s bytes.
  roofline   the headline kernel against measured HBM bandwidth (bytes defined in roofline()).
+ materialised
+            the same inputs through mode 0 (every ballot materialised: SURVEY 8(d)'s bytes), rated on those bytes.
  cpu_baseline / --impl reference
             the reference's own C++ (oracle/_ref, else the port) on all host cores, bounded sample.
 """
@@ -328,6 +330,8 @@ def main():
     if not args.single_mode:
         om = 0 if stats["mode"] >= 1 else 1
         o_epg = max(296, epg // 8) if om == 0 else epg
+        if om == 0 and o_epg > 1776:
+            o_epg -= o_epg % 1776  # whole waves of the three phase kernels (12 elections per SM)
         other = measure(t, cfg, om, o_epg, max(2, min(args.steps, 3)), 3, 1 << 40, 0.0, 1)
     t.tune(mode=args.mode)
 
@@ -511,8 +515,11 @@ def main():
         key = "materialised" if other["kernel"] == "simulate_kernel" else "deferred"
         line[key] = {"kernel": other["kernel"], "value": other["value"], "unit": "elections/s", "steps": other["steps"],
                      "elections_per_gpu_per_step": other["elections_per_gpu"],
+                     "launches_per_job": int(other["launches_per_job"]),
                      "roofline": roofline(other, b_alg, nc, name if args.gamma is None else None),
-                     "note": "same inputs and seed; outcomes are bit-identical to the headline kernel's"}
+                     "note": "same inputs and seed; outcomes are bit-identical to the headline kernel's. mode 0 runs a job of "
+                             "more than two machine-fulls of elections as waves of three launches (sim_big_kernel, "
+                             "sim_walk_kernel, sim_irv_kernel: DESIGN.md 5.2); kernel_ms is the whole job"}
     if workloads is not None:
         line["workloads"] = workloads
     print(json.dumps(line))

@@ -210,7 +210,10 @@ int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user
  *        arena (mode 1) and hand-over to the replay launch (mode 2); results do not change);
  *      "lane_max_splits" (-1 default = chosen from the node splits an election typically needs; 0 = no limit;
  *        n > 0 = in mode 2 an election that needs more than n node splits is handed to the replay launch, where a
- *        whole warp finishes it, instead of keeping its thread — and the launch — busy; results do not change).
+ *        whole warp finishes it, instead of keeping its thread — and the launch — busy; results do not change);
+ *      "sim_phased" (-1 default: mode 0 runs a job of more than two machine-fulls of elections as waves of three
+ *        launches — level loop, small-subtree walkers, IRV stage, each at its own occupancy — instead of one
+ *        persistent kernel; 0 never; 1 whenever an election is followed by IRV; results do not change).
  * Returns DTREE_ERR_ARG for an unknown key. */
 int dtree_set_tuning(dtree_t *t, const char *key, int64_t value);
 /* Statistics of the last sampling call on this handle (counters restart at every call; [7] and [14] describe the
