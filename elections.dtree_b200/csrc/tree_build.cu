@@ -7,6 +7,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
 
 namespace dtb {
 
@@ -23,8 +24,14 @@ void DeviceTreeStore::release_all() {
 
 namespace {
 
-constexpr int kScanBlock = 256;
-constexpr int kScanItems = 8;
+#ifndef DTB_SCAN_BLOCK
+#define DTB_SCAN_BLOCK 512
+#endif
+constexpr int kScanBlock = DTB_SCAN_BLOCK;
+#ifndef DTB_SCAN_ITEMS
+#define DTB_SCAN_ITEMS 1
+#endif
+constexpr int kScanItems = DTB_SCAN_ITEMS;
 constexpr int kScanTile = kScanBlock * kScanItems;
 constexpr uint32_t kDone = 0xFFFFFFFFu;
 // Level table (device memory, so that no level has to wait for the host): row d = {first node, nodes, first slot, -}
@@ -207,6 +214,34 @@ __global__ void __launch_bounds__(kScanBlock)
 
 // Numbers the children of a level and initialises them: slots, candidates (the parent's order with the
 // taken candidate swapped to the front, irv_node.cpp:219), prefix key.
+// A new node for slot j of parent pn (its slots start at pbase): its candidates are the parent's with the chosen one
+// swapped to the front and dropped (irv_node.cpp:219). The parent's candidates are read before anything is written, so
+// the loads are in flight together instead of alternating with stores to the same array.
+__device__ __forceinline__ void write_child(const TreePtrs &T, uint32_t slot, uint32_t pbase, uint32_t j, uint32_t K,
+                                            uint32_t child, uint32_t cbase, uint32_t parent, uint32_t depth, int W) {
+  uint8_t pc[kMaxCandidates + 1];
+#pragma unroll 8
+  for (uint32_t q = 0; q < K; ++q) pc[q] = T.slot_cand[pbase + q];
+  uint64_t pk[kMaxKeyWords];
+  for (int w = 0; w < W; ++w) pk[w] = T.node_key[(size_t)parent * W + w];
+  T.slot_child[slot] = (int32_t)child;
+  T.node_base[child] = cbase;
+  for (uint32_t q = 0; q + 1 < K; ++q) {
+    T.slot_cand[cbase + q] = (q + 1 == j) ? pc[0] : pc[q + 1];
+    T.slot_child[cbase + q] = -1;
+    T.slot_count[cbase + q] = 0;
+  }
+  T.slot_cand[cbase + K - 1] = 0xFF;
+  T.slot_child[cbase + K - 1] = -1;
+  T.slot_count[cbase + K - 1] = 0;
+  const uint64_t cand = pc[j];
+  for (int w = 0; w < W; ++w) {
+    uint64_t key = pk[w];
+    if ((int)(depth / kPrefsPerWord) == w) key |= cand << (kPrefBits * (depth % kPrefsPerWord));
+    T.node_key[(size_t)child * W + w] = key;
+  }
+}
+
 __global__ void __launch_bounds__(kScanBlock)
     create_children_kernel(TreePtrs T, LevelFlag f, const uint32_t *__restrict__ tab, const uint32_t *__restrict__ block_sums,
                            uint32_t depth, int W) {
@@ -232,28 +267,15 @@ __global__ void __launch_bounds__(kScanBlock)
     const uint32_t slot = row[2] + i, pbase = row[2] + pn * f.per_node;
     const uint32_t child = first_new_node + rank, cbase = new_slot_base + rank * K;
     ++rank;
-    T.slot_child[slot] = (int32_t)child;
-    T.node_base[child] = cbase;
-    for (uint32_t q = 0; q + 1 < K; ++q) {
-      T.slot_cand[cbase + q] = (q + 1 == j) ? T.slot_cand[pbase] : T.slot_cand[pbase + q + 1];
-      T.slot_child[cbase + q] = -1;
-      T.slot_count[cbase + q] = 0;
-    }
-    T.slot_cand[cbase + K - 1] = 0xFF;
-    T.slot_child[cbase + K - 1] = -1;
-    T.slot_count[cbase + K - 1] = 0;
-    const uint32_t parent = level_first_node + pn;
-    const uint64_t cand = T.slot_cand[slot];
-    for (int w = 0; w < W; ++w) {
-      uint64_t key = T.node_key[(size_t)parent * W + w];
-      if ((int)(depth / kPrefsPerWord) == w) key |= cand << (kPrefBits * (depth % kPrefsPerWord));
-      T.node_key[(size_t)child * W + w] = key;
-    }
+    write_child(T, slot, pbase, j, K, child, cbase, level_first_node + pn, depth, W);
   }
 }
 
-__global__ void node_totals_kernel(TreePtrs T, const uint32_t *__restrict__ tab) {
+// Also the first-preference tallies of the observed ballots: slot c of the root is candidate c, and every ballot with a
+// first preference was counted there (one copy of nc words instead of one contended atomic per observed entry).
+__global__ void node_totals_kernel(TreePtrs T, const uint32_t *__restrict__ tab, uint32_t *obs_tally0, uint32_t nc) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nc) obs_tally0[i] = T.slot_count[i];
   if (i >= tab[4 * kTotRow]) return;
   const uint32_t base = T.node_base[i], K = T.node_base[i + 1] - base - 1u;
   uint32_t s = 0;
@@ -277,7 +299,6 @@ __device__ void write_observed(const TreePtrs &T, const ObsOut &O, uint32_t at, 
   if (L > 0) {
     first = key_get<kMaxKeyWords>(k, 0);
     for (uint32_t j = L; j < nc - 1u; ++j) key_set<kMaxKeyWords>(k, (int)j, first);  // capi.cu pack_ballot
-    atomicAdd(&O.tally0[first], count);
   }
   for (int w = 0; w < W; ++w) O.key[(size_t)at * W + w] = k.w[w];
   O.cnt[at] = count;
@@ -347,21 +368,36 @@ __device__ __forceinline__ void tile_sum_phase(F f, uint32_t n, uint32_t *block_
   }
 }
 
-// Exclusive scan of block_sums[0..nb) in place by the calling block; returns the total to every thread.
-__device__ __forceinline__ uint32_t scan_tiles(uint32_t *block_sums, uint32_t nb) {
-  uint32_t carry = 0;
-  for (uint32_t start = 0; start < nb; start += kScanBlock) {
-    const uint32_t i = start + threadIdx.x;
-    const uint32_t v = i < nb ? block_sums[i] : 0u;
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan(v, &total);
-    if (i < nb) block_sums[i] = carry + ex;
-    carry += total;
-  }
-  return carry;
+// Sum of block_sums[0..nb), to every thread of the calling block.
+__device__ __forceinline__ uint32_t sum_tiles(const uint32_t *block_sums, uint32_t nb) {
+  uint32_t v = 0;
+  for (uint32_t i = threadIdx.x; i < nb; i += kScanBlock) v += block_sums[i];
+  uint32_t total;
+  block_exclusive_scan(v, &total);
+  return total;
 }
 
+#ifndef DTB_COUNT_UNROLL
+#define DTB_COUNT_UNROLL 1  // 2 and 3 measured: 0.188 / 0.184 ms against 0.174
+#endif
+constexpr int kCountUnroll = DTB_COUNT_UNROLL;
 constexpr int kCountBins = 8192;  // outcome slots of a level counted in shared memory (32 KB)
+
+// Profiling build (-DDTB_BUILD_CLOCKS): block 0 prints the time between the grid-wide barriers of a few rebuilds.
+#ifdef DTB_BUILD_CLOCKS
+__device__ int g_build_prints = 0;
+#define DTB_STAMP(tag)                                                                   \
+  do {                                                                                   \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_ts < 96) {                              \
+      unsigned long long t_;                                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+      ts[n_ts] = t_;                                                                     \
+      tg[n_ts++] = (tag);                                                                \
+    }                                                                                    \
+  } while (0)
+#else
+#define DTB_STAMP(tag)
+#endif
 
 __global__ void __launch_bounds__(kScanBlock) build_tree_coop_kernel(const CoopArgs A) {
   __shared__ uint32_t s_bins[kCountBins];
@@ -371,6 +407,11 @@ __global__ void __launch_bounds__(kScanBlock) build_tree_coop_kernel(const CoopA
   const uint64_t n = A.n_ballots;
   const uint64_t gsize = (uint64_t)gridDim.x * kScanBlock, gtid = (uint64_t)blockIdx.x * kScanBlock + tid;
   uint32_t *tab = A.tab;
+#ifdef DTB_BUILD_CLOCKS
+  unsigned long long ts[96];
+  int tg[96], n_ts = 0;
+#endif
+  DTB_STAMP(0);
 
   // phase 0: slot sequences of the new ballots (slot_sequences_kernel) and the root (init_root_kernel)
   for (uint64_t b = A.first_new + gtid; b < n; b += gsize) {
@@ -408,6 +449,7 @@ __global__ void __launch_bounds__(kScanBlock) build_tree_coop_kernel(const CoopA
     }
   }
   grid.sync();
+  DTB_STAMP(1);
 
   for (uint32_t depth = 0;; ++depth) {
     const uint32_t K = nc - depth;
@@ -422,31 +464,41 @@ __global__ void __launch_bounds__(kScanBlock) build_tree_coop_kernel(const CoopA
       for (uint32_t i = tid; i < lvl_slots; i += kScanBlock) s_bins[i] = 0;
       __syncthreads();
     }
-    for (uint64_t b0 = (uint64_t)blockIdx.x * kScanBlock; b0 < n; b0 += gsize) {
-      const uint64_t b = b0 + tid;
-      uint32_t idx = kDone;
-      if (b < n) {
-        const uint32_t cur = depth == 0 ? 0u : A.cursor[b];
-        if (cur != kDone) {
-          const uint32_t node = depth == 0 ? 0u : (uint32_t)T.slot_child[cur];
-          const uint32_t base = T.node_base[node];
-          const uint64_t lo = A.off[b];
-          const uint32_t len = (uint32_t)(A.off[b + 1] - lo);
-          if (len == depth) {  // irv_node.cpp:191-194
-            idx = base + K;
-            A.cursor[b] = kDone;
-          } else {
-            idx = base + A.slots[lo + depth];
-            A.cursor[b] = K == 2 ? kDone : idx;  // irv_node.cpp:210
+    // kCountUnroll ballots per thread and step: all their loads (cursor -> child -> node base, offsets, slot) are issued
+    // before anything is stored, so the dependent-load chains of a thread's ballots overlap instead of following
+    // each other.
+    for (uint64_t b0 = (uint64_t)blockIdx.x * kScanBlock; b0 < n; b0 += kCountUnroll * gsize) {
+      uint32_t idx[kCountUnroll], next_cur[kCountUnroll];
+#pragma unroll
+      for (int u = 0; u < kCountUnroll; ++u) {
+        const uint64_t b = b0 + (uint64_t)u * gsize + tid;
+        idx[u] = kDone;
+        next_cur[u] = kDone;
+        if (b < n) {
+          const uint32_t cur = depth == 0 ? 0u : A.cursor[b];
+          if (cur != kDone) {
+            const uint32_t node = depth == 0 ? 0u : (uint32_t)T.slot_child[cur];
+            const uint32_t base = T.node_base[node];
+            const uint64_t lo = A.off[b];
+            const uint32_t len = (uint32_t)(A.off[b + 1] - lo);
+            if (len == depth) {  // irv_node.cpp:191-194
+              idx[u] = base + K;
+            } else {
+              idx[u] = base + A.slots[lo + depth];
+              next_cur[u] = K == 2 ? kDone : idx[u];  // irv_node.cpp:210
+            }
           }
-        } else if (depth == 0) {
-          A.cursor[b] = kDone;
         }
       }
-      const unsigned peers = __match_any_sync(0xFFFFFFFFu, idx);
-      if (idx != kDone && (tid & 31) == (unsigned)(__ffs(peers) - 1)) {
-        if (privatise) atomicAdd(&s_bins[idx - lvl_base], (uint32_t)__popc(peers));
-        else atomicAdd(&T.slot_count[idx], (uint32_t)__popc(peers));
+#pragma unroll
+      for (int u = 0; u < kCountUnroll; ++u) {
+        const uint64_t b = b0 + (uint64_t)u * gsize + tid;
+        if (b < n && (idx[u] != kDone || depth == 0)) A.cursor[b] = next_cur[u];
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, idx[u]);
+        if (idx[u] != kDone && (tid & 31) == (unsigned)(__ffs(peers) - 1)) {
+          if (privatise) atomicAdd(&s_bins[idx[u] - lvl_base], (uint32_t)__popc(peers));
+          else atomicAdd(&T.slot_count[idx[u]], (uint32_t)__popc(peers));
+        }
       }
     }
     if (privatise) {
@@ -456,30 +508,36 @@ __global__ void __launch_bounds__(kScanBlock) build_tree_coop_kernel(const CoopA
     }
     if (K <= 2 || n == 0) break;  // irv_node.cpp:210: a node with two candidates left has no children
     grid.sync();
+    DTB_STAMP(10 + (int)depth);  // count
     const uint32_t *row = tab + 4 * depth;
     const uint32_t level_nodes = row[1];
     if (level_nodes == 0) break;
     const uint32_t n_items = level_nodes * (K + 1);
     const uint32_t n_tiles = (n_items + kScanTile - 1) / kScanTile;
     LevelFlag f{T.slot_count, row, K + 1};
-    tile_sum_phase(f, n_items, A.block_sums);
+    // (Counting the new children per tile inside the count phase - the thread whose atomic finds a slot at 0 adds one
+    // to its tile - would save this phase and its barrier, but at the deep levels nearly every ballot opens a slot and
+    // those extra atomics land on a few hundred counters: 0.174 -> 0.189 ms. Measured and dropped.)
+    uint32_t *sums = A.block_sums;
+    tile_sum_phase(f, n_items, sums);
     grid.sync();
-    if (blockIdx.x == 0) {  // scan_sums_kernel
-      const uint32_t carry = scan_tiles(A.block_sums, n_tiles);
-      if (tid == 0) {
-        uint32_t *tot = tab + 4 * kTotRow, *next = tab + 4 * (depth + 1);
-        next[0] = row[0] + row[1];
-        next[1] = carry;
-        next[2] = row[2] + row[1] * (K + 1);
-        tot[0] = next[0] + carry;
-        tot[1] = next[2] + carry * K;  // a child has one slot less than its parent
-      }
+    DTB_STAMP(100 + (int)depth);  // tile sums
+    // scan_sums_kernel without its own barrier: there are at most a few hundred tile sums, so every block adds up
+    // the ones it needs itself - all of them for the size of the next level, those before a tile for that tile's
+    // first rank - and only block 0 writes the level table (read again after the next barrier).
+    const uint32_t carry = sum_tiles(sums, n_tiles);
+    const uint32_t level_first_node = row[0], first_new_node = row[0] + row[1], n_new = carry;
+    const uint32_t new_slot_base = row[2] + row[1] * (K + 1);
+    if (blockIdx.x == 0 && tid == 0) {
+      uint32_t *tot = tab + 4 * kTotRow, *next = tab + 4 * (depth + 1);
+      next[0] = first_new_node;
+      next[1] = carry;
+      next[2] = new_slot_base;
+      tot[0] = first_new_node + carry;
+      tot[1] = new_slot_base + carry * K;  // a child has one slot less than its parent
+      T.node_base[first_new_node + n_new] = new_slot_base + n_new * K;
     }
-    grid.sync();
     {  // create_children_kernel
-      const uint32_t *next = row + 4;
-      const uint32_t level_first_node = row[0], first_new_node = next[0], n_new = next[1], new_slot_base = next[2];
-      if (blockIdx.x == 0 && tid == 0) T.node_base[first_new_node + n_new] = new_slot_base + n_new * K;
       for (uint32_t vb = blockIdx.x; vb < n_tiles; vb += gridDim.x) {
         const uint32_t first = vb * (uint32_t)kScanTile + tid * (uint32_t)kScanItems;
         uint32_t flags = 0, s = 0;
@@ -489,39 +547,27 @@ __global__ void __launch_bounds__(kScanBlock) build_tree_coop_kernel(const CoopA
             flags |= 1u << k;
             ++s;
           }
+        const uint32_t before = sum_tiles(sums, vb);
         uint32_t total;
-        uint32_t rank = block_exclusive_scan(s, &total) + A.block_sums[vb];
+        uint32_t rank = block_exclusive_scan(s, &total) + before;
         for (int k = 0; k < kScanItems; ++k) {
           if (!(flags >> k & 1u)) continue;
           const uint32_t i = first + k, pn = i / (K + 1), j = i % (K + 1);
           const uint32_t slot = row[2] + i, pbase = row[2] + pn * (K + 1);
           const uint32_t child = first_new_node + rank, cbase = new_slot_base + rank * K;
           ++rank;
-          T.slot_child[slot] = (int32_t)child;
-          T.node_base[child] = cbase;
-          for (uint32_t q = 0; q + 1 < K; ++q) {
-            T.slot_cand[cbase + q] = (q + 1 == j) ? T.slot_cand[pbase] : T.slot_cand[pbase + q + 1];
-            T.slot_child[cbase + q] = -1;
-            T.slot_count[cbase + q] = 0;
-          }
-          T.slot_cand[cbase + K - 1] = 0xFF;
-          T.slot_child[cbase + K - 1] = -1;
-          T.slot_count[cbase + K - 1] = 0;
-          const uint32_t parent = level_first_node + pn;
-          const uint64_t cand = T.slot_cand[slot];
-          for (int w = 0; w < A.W; ++w) {
-            uint64_t key = T.node_key[(size_t)parent * A.W + w];
-            if ((int)(depth / kPrefsPerWord) == w) key |= cand << (kPrefBits * (depth % kPrefsPerWord));
-            T.node_key[(size_t)child * A.W + w] = key;
-          }
+          write_child(T, slot, pbase, j, K, child, cbase, level_first_node + pn, depth, A.W);
         }
       }
     }
     grid.sync();
+    DTB_STAMP(300 + (int)depth);  // children
   }
   grid.sync();
+  DTB_STAMP(400);
   // node totals and the packed observed multiset (node_totals_kernel, tile/scan, write_observed_kernel)
   const uint32_t n_nodes = tab[4 * kTotRow];
+  if (gtid < nc) A.obs_tally0[gtid] = T.slot_count[gtid];  // first-preference tallies = the root's slot counts
   for (uint64_t i = gtid; i < n_nodes; i += gsize) {
     const uint32_t base = T.node_base[i], K = T.node_base[i + 1] - base - 1u;
     uint32_t s = 0;
@@ -531,20 +577,21 @@ __global__ void __launch_bounds__(kScanBlock) build_tree_coop_kernel(const CoopA
   ObservedFlag of{T.node_base, T.slot_count};
   tile_sum_phase(of, n_nodes, A.block_sums);
   grid.sync();
+  DTB_STAMP(401);
   const uint32_t node_tiles = (n_nodes + kScanTile - 1) / kScanTile;
-  if (blockIdx.x == 0) {
-    const uint32_t carry = scan_tiles(A.block_sums, node_tiles);
+  if (blockIdx.x == 0) {  // the number of observed entries; each block sums the tiles before its own itself
+    const uint32_t carry = sum_tiles(A.block_sums, node_tiles);
     if (tid == 0) tab[4 * kTotRow + 2] = carry;
   }
-  grid.sync();
   for (uint32_t vb = blockIdx.x; vb < node_tiles; vb += gridDim.x) {
     const uint32_t first = vb * (uint32_t)kScanTile + tid * (uint32_t)kScanItems;
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
       if (first + k < n_nodes) s += of(first + k);
+    const uint32_t before = sum_tiles(A.block_sums, vb);
     uint32_t total;
-    uint32_t at = block_exclusive_scan(s, &total) + A.block_sums[vb];
+    uint32_t at = block_exclusive_scan(s, &total) + before;
     if (s == 0) continue;
     for (int k = 0; k < kScanItems; ++k) {
       const uint32_t i = first + k;
@@ -559,6 +606,14 @@ __global__ void __launch_bounds__(kScanBlock) build_tree_coop_kernel(const CoopA
         }
     }
   }
+#ifdef DTB_BUILD_CLOCKS
+  DTB_STAMP(403);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int k = atomicAdd(&g_build_prints, 1);
+    if (k >= 20 && k < 22)
+      for (int i = 1; i < n_ts; ++i) printf("build %d phase %d: %llu ns\n", k, tg[i], ts[i] - ts[i - 1]);
+  }
+#endif
 }
 
 #define BUILD_TRY(expr)              \
@@ -764,7 +819,7 @@ cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t 
     nodes_launch = S.h_tab[4 * kTotRow];
     BUILD_TRY(S.node_total.grow(nodes_launch, 0, stream));
   }
-  node_totals_kernel<<<(nodes_launch + 255) / 256, 256, 0, stream>>>(ptrs(S), tab);
+  node_totals_kernel<<<(nodes_launch + 255) / 256, 256, 0, stream>>>(ptrs(S), tab, S.obs_tally0.p, nc);
   const uint32_t nb = (nodes_launch + kScanTile - 1) / kScanTile;
   BUILD_TRY(S.block_sums.grow(nb, 0, stream));
   ObservedFlag of{S.node_base.p, S.slot_count.p};
