@@ -332,7 +332,12 @@ def main():
         o_epg = max(296, epg // 8) if om == 0 else epg
         if om == 0 and o_epg > 1776:
             o_epg -= o_epg % 1776  # whole waves of the three phase kernels (12 elections per SM)
-        other = measure(t, cfg, om, o_epg, max(2, min(args.steps, 3)), 3, 1 << 40, 0.0, 1)
+        # on a handle of its own, destroyed afterwards: the materialising path reserves tens of GB of per-election
+        # scratch, which would otherwise stay with `t` and shrink what the later legs may plan with
+        t_other, _ = make_tree(name, cfg, (prefs, offsets))
+        other = measure(t_other, cfg, om, o_epg, max(2, min(args.steps, 3)), 3, 1 << 40, 0.0, 1)
+        del t_other
+        torch.cuda.empty_cache()
     t.tune(mode=args.mode)
 
     # ---- identity + strong scaling: ONE fixed job sharded over the ranks ----------------------------------------------

@@ -194,6 +194,7 @@ struct dtree {
   uint32_t binv_max = 30;        // binomials with n p below this use inversion, the others BTRS
   uint32_t last_lane_retries = 0;  // elections lane_kernel handed to its replay in the last call read back
   uint64_t mem_avail = 0;        // device bytes the plans may use (free + held by this handle), as last queried
+  uint32_t lane_width = 0;  // lane_kernel: elections per warp (0: chosen per job)
   int sim_phased = -1;  // materialising path as three launches per wave: -1 when it pays off, 0 never, 1 always
   int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
   // replicas on other devices for dtree_sample_posterior_multi (owned; same parameters, tree copied when stale)
@@ -313,6 +314,7 @@ struct Plan {
   int W, block, grid, blocks_per_sm;
   bool log_gamma;
   uint32_t cap_items, cap_entries, cap_queue = 0, cap_big = 0, cap_small = 0;
+  uint32_t lane_width = 32;  // lane_kernel: elections per warp
   bool phased = false;  // simulate_kernel's work as three launches per wave of `grid` elections (sim_*_kernel)
   uint32_t n_arenas = 0, arena_items = 0, arena_queue = 0, arena_big = 0;
   uint64_t arena_stride = 0, mem_budget = 0;
@@ -465,6 +467,7 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
   a.scratch_stride = pl.stride;
   a.cap_items = pl.cap_items;
   a.cap_small = pl.cap_small;
+  a.lane_width = pl.lane_width;
   a.cap_entries = pl.cap_entries;
   a.cap_queue = pl.cap_queue;
   a.cap_big = pl.cap_big;
@@ -776,7 +779,14 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
       if (t->blocks_per_sm > 0) occ = std::min(occ, t->blocks_per_sm);
       const uint64_t resident = (uint64_t)occ * t->sm_count;
       const uint64_t fit = std::max<uint64_t>(1, pl.mem_budget / lp.stride_block);
-      const uint64_t need = ((uint64_t)(n_elections - pilot_done) + lp.block - 1) / lp.block;
+      // Elections per warp: 32 unless the tuning key lane_width says otherwise. Measured (tools/width_probe.py, C3): a
+      // warp's batch takes ~0.4 ms however few of its lanes work (one election alone is a 0.25 ms chain of dependent
+      // variates), so spreading a small job over more, narrower warps buys at most 5 % (12 500 elections: 0.436 ms at
+      // 32 per warp, 0.412 at 8, 0.53 at 4) and costs a lot once the warps outnumber the schedulers' appetite.
+      const uint64_t todo = (uint64_t)(n_elections - pilot_done);
+      lp.lane_width = t->lane_width ? t->lane_width : 32u;
+      const uint64_t per_block = (uint64_t)lp.lane_width * (lp.block / 32);
+      const uint64_t need = (todo + per_block - 1) / per_block;
       lp.grid = (int)std::max<uint64_t>(1, std::min(std::min(resident, fit), need));
       if (t->mode < 0) {
         // Automatic choice: a thread per election pays off when there are enough elections to fill the machine
@@ -1314,6 +1324,7 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
     r->host_build = t->host_build;
     r->build_mode = t->build_mode;
     r->sim_phased = t->sim_phased;
+    r->lane_width = t->lane_width;
     r->mode = t->mode;
     r->urn_max = t->urn_max;
     r->block_threads = t->block_threads;
@@ -1578,6 +1589,9 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   } else if (!strcmp(key, "lane_max_splits")) {
     if (value < -1) return fail(DTREE_ERR_ARG, "lane_max_splits must be -1 (auto), 0 (no limit) or a positive count");
     t->lane_max_splits = value;
+  } else if (!strcmp(key, "lane_width")) {
+    if (value < 0 || value > 32) return fail(DTREE_ERR_ARG, "lane_width must be 0 (auto) or 1..32");
+    t->lane_width = (uint32_t)value;
   } else if (!strcmp(key, "sim_phased")) {
     if (value < -1 || value > 1) return fail(DTREE_ERR_ARG, "sim_phased must be -1 (auto), 0 or 1");
     t->sim_phased = (int)value;

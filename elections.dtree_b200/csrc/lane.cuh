@@ -336,13 +336,14 @@ __global__ void __launch_bounds__(BLOCK, DTB_LANE_THREADS_PER_SM / BLOCK) lane_k
   const bool early_stop = a.n_winners == 1u && a.elim_orders == nullptr;
 
   for (;;) {
-    // the 32 elections of a warp are claimed, and finished, together
+    // the elections of a warp are claimed, and finished, together: 32 of them, or fewer (a.lane_width) when the job
+    // has too few elections to fill the machine that way - a warp's time grows with the number of lanes that diverge
     uint32_t base = 0;
-    if (lane == 0u) base = atomicAdd(a.work_counter, 32u);
+    if (lane == 0u) base = atomicAdd(a.work_counter, a.lane_width);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= a.n_elections) break;
     const uint32_t e = base + lane;
-    const bool active = e < a.n_elections;
+    const bool active = lane < a.lane_width && e < a.n_elections;
     const RngKey key = election_key(a.seed, a.first_election + e);
     LaneState st;
     st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.n_top = 0; st.eliminated = 0;
