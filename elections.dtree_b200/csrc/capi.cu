@@ -966,18 +966,27 @@ int run_dump(dtree *t, uint64_t election, uint32_t n_sample, const char *seed, s
   std::vector<uint64_t> keys((size_t)n * W + 1);
   std::vector<uint32_t> cnt(n + 1);
   std::vector<uint8_t> len(n + 1);
-  // scratch layout of block 0 (Scratch<W>::bind)
+  // scratch layout of block 0 (Scratch<W>::bind): the entries are records of W key words + count + length
   uint8_t *base = t->d_scratch.p;
-  uint8_t *p_key, *p_cnt, *p_len;
-  if (W == 1) { Scratch<1> sc; sc.bind(base, pl.cap_items, pl.cap_entries, pl.cap_small); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
-  else if (W == 2) { Scratch<2> sc; sc.bind(base, pl.cap_items, pl.cap_entries, pl.cap_small); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
-  else { Scratch<3> sc; sc.bind(base, pl.cap_items, pl.cap_entries, pl.cap_small); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
+  uint8_t *p_ent;
+  if (W == 1) { Scratch<1> sc; sc.bind(base, pl.cap_items, pl.cap_entries, pl.cap_small); p_ent = (uint8_t *)sc.ent; }
+  else if (W == 2) { Scratch<2> sc; sc.bind(base, pl.cap_items, pl.cap_entries, pl.cap_small); p_ent = (uint8_t *)sc.ent; }
+  else { Scratch<3> sc; sc.bind(base, pl.cap_items, pl.cap_entries, pl.cap_small); p_ent = (uint8_t *)sc.ent; }
+  const size_t rec = (size_t)W * 8 + 8;
   if (n) {
-    CUDA_TRY(cudaMemcpy(keys.data(), p_key, (size_t)n * W * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(cnt.data(), p_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(len.data(), p_len, (size_t)n, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> raw((size_t)n * rec);
+    CUDA_TRY(cudaMemcpy(raw.data(), p_ent, raw.size(), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint8_t *r = raw.data() + (size_t)i * rec;
+      memcpy(&keys[(size_t)i * W], r, (size_t)W * 8);
+      uint32_t c, l;
+      memcpy(&c, r + (size_t)W * 8, 4);
+      memcpy(&l, r + (size_t)W * 8 + 4, 4);
+      cnt[i] = c;
+      len[i] = (uint8_t)l;
+    }
   }
-  t->stats[kOutD2H] += (uint64_t)n * (W * 8 + 5);
+  t->stats[kOutD2H] += (uint64_t)n * rec;
   // The kernel appends entries in whatever order its warps finish, which varies from launch to launch; the list is
   // returned in a canonical order (by ballot, lexicographic in the candidate indices, a prefix before its
   // extensions) so that the same seed gives the same R object (tests/testthat/test-determinism.R:5-22).
@@ -1514,15 +1523,22 @@ int dtree_irv(const uint8_t *prefs, const uint64_t *offsets, const uint32_t *cou
   cudaError_t e = scratch.reserve(bytes);
   if (e == cudaSuccess) e = d_order.reserve(kMaxCandidates);
   if (e == cudaSuccess) e = d_ties.reserve(1);
-  uint8_t *p_key = nullptr, *p_cnt = nullptr, *p_len = nullptr;
   if (e == cudaSuccess) {
-    if (W == 1) { Scratch<1> sc; sc.bind(scratch.p, 0, cap); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
-    else if (W == 2) { Scratch<2> sc; sc.bind(scratch.p, 0, cap); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
-    else { Scratch<3> sc; sc.bind(scratch.p, 0, cap); p_key = (uint8_t *)sc.ent_key; p_cnt = (uint8_t *)sc.ent_cnt; p_len = sc.ent_len; }
-    if (n) {
-      e = cudaMemcpy(p_key, keys.data(), n * W * 8, cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) e = cudaMemcpy(p_cnt, counts, n * 4, cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) e = cudaMemcpy(p_len, lens.data(), n, cudaMemcpyHostToDevice);
+    uint8_t *p_ent;
+    if (W == 1) { Scratch<1> sc; sc.bind(scratch.p, 0, cap); p_ent = (uint8_t *)sc.ent; }
+    else if (W == 2) { Scratch<2> sc; sc.bind(scratch.p, 0, cap); p_ent = (uint8_t *)sc.ent; }
+    else { Scratch<3> sc; sc.bind(scratch.p, 0, cap); p_ent = (uint8_t *)sc.ent; }
+    if (n) {  // entry records: W key words, count, length (Entry<W>)
+      const size_t rec = (size_t)W * 8 + 8;
+      std::vector<uint8_t> raw((size_t)n * rec);
+      for (uint64_t i = 0; i < n; ++i) {
+        uint8_t *r = raw.data() + (size_t)i * rec;
+        memcpy(r, &keys[i * W], (size_t)W * 8);
+        const uint32_t c = counts[i], l = lens[i];
+        memcpy(r + (size_t)W * 8, &c, 4);
+        memcpy(r + (size_t)W * 8 + 4, &l, 4);
+      }
+      e = cudaMemcpy(p_ent, raw.data(), raw.size(), cudaMemcpyHostToDevice);
     }
   }
   if (e == cudaSuccess) {

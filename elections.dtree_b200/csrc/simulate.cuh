@@ -39,31 +39,37 @@ constexpr int kClkSlots = 0;
 #endif
 
 // Where the pieces of one block's scratch live.
+// One sampled (ballot, count) entry: a single 16-byte record for keys of one word (24 / 32 bytes for two / three), so that
+// writing an entry is one store and re-examining it in the IRV stage touches one 32-byte sector instead of three.
+template <int W>
+struct alignas(W == 2 ? 8 : 16) Entry {
+  BallotKey<W> key;
+  uint32_t cnt;
+  uint32_t len;
+};
+
+static_assert(sizeof(Entry<1>) == 16 && sizeof(Entry<2>) == 24 && sizeof(Entry<3>) == 32, "capi.cu packs these records");
+
 template <int W>
 struct Scratch {
   uint32_t *hdr;       // kHdr* words: what one phase kernel hands to the next (phased launches)
   Item<W> *small;      // items with count <= urn_max, all depths: walked to completion after the level loop
   Item<W> *frontier[2];
-  BallotKey<W> *ent_key;
-  uint32_t *ent_cnt;
-  uint8_t *ent_len;
+  Entry<W> *ent;
   uint8_t *ent_holder;
   uint8_t *obs_holder;
   __host__ __device__ static uint64_t align16(uint64_t x) { return (x + 15) & ~15ull; }
   __host__ __device__ static uint64_t bytes(uint32_t cap_items, uint32_t cap_entries, uint32_t n_obs,
                                             uint32_t cap_small = 0) {
     return 16 + align16((uint64_t)cap_small * sizeof(Item<W>)) + 2 * align16((uint64_t)cap_items * sizeof(Item<W>)) +
-           align16((uint64_t)cap_entries * sizeof(BallotKey<W>)) + align16((uint64_t)cap_entries * 4) +
-           2 * align16(cap_entries) + align16(n_obs);
+           align16((uint64_t)cap_entries * sizeof(Entry<W>)) + align16(cap_entries) + align16(n_obs);
   }
   __host__ __device__ void bind(uint8_t *p, uint32_t cap_items, uint32_t cap_entries, uint32_t cap_small = 0) {
     hdr = (uint32_t *)p; p += 16;
     small = (Item<W> *)p; p += align16((uint64_t)cap_small * sizeof(Item<W>));
     frontier[0] = (Item<W> *)p; p += align16((uint64_t)cap_items * sizeof(Item<W>));
     frontier[1] = (Item<W> *)p; p += align16((uint64_t)cap_items * sizeof(Item<W>));
-    ent_key = (BallotKey<W> *)p; p += align16((uint64_t)cap_entries * sizeof(BallotKey<W>));
-    ent_cnt = (uint32_t *)p; p += align16((uint64_t)cap_entries * 4);
-    ent_len = p; p += align16(cap_entries);
+    ent = (Entry<W> *)p; p += align16((uint64_t)cap_entries * sizeof(Entry<W>));
     ent_holder = p; p += align16(cap_entries);
     obs_holder = p;
   }
@@ -269,9 +275,11 @@ __device__ void walk_small_items(const SimArgs &a, Scratch<W> &sc, SharedFixed<B
       }
       if (dest == 3) {
         if (at < a.cap_entries) {
-          sc.ent_key[at] = pk;
-          sc.ent_cnt[at] = c;
-          sc.ent_len[at] = (uint8_t)(stop ? lv.depth : lv.depth + 1);
+          Entry<W> en;
+          en.key = pk;
+          en.cnt = c;
+          en.len = stop ? lv.depth : lv.depth + 1;
+          sc.ent[at] = en;
         } else {
           sm.overflow = 1;
         }
@@ -339,9 +347,11 @@ __device__ void expand_chunk(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
     }
     if (dest == 1) {
       if (eo < a.cap_entries) {
-        sc.ent_key[eo] = pk;
-        sc.ent_cnt[eo] = c;
-        sc.ent_len[eo] = (uint8_t)(slot == K ? lv.depth : lv.depth + 1);
+        Entry<W> en;
+        en.key = pk;
+        en.cnt = c;
+        en.len = slot == K ? lv.depth : lv.depth + 1;
+        sc.ent[eo] = en;
       } else {
         sm.overflow = 1;
       }
@@ -512,9 +522,10 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
       cnt[u] = 0;
       first[u] = 0;
       if (i < n_ent) {
-        len[u] = sc.ent_len[i];
-        first[u] = (uint32_t)sc.ent_key[i].w[0] & 31u;
-        cnt[u] = sc.ent_cnt[i];
+        const Entry<W> en = sc.ent[i];
+        len[u] = en.len;
+        first[u] = (uint32_t)en.key.w[0] & 31u;
+        cnt[u] = en.cnt;
       }
     }
 #pragma unroll
@@ -610,8 +621,9 @@ __device__ void irv_election(const SimArgs &a, Scratch<W> &sc, SharedFixed<BLOCK
             if (i >= n_part) break;
             uint32_t cand, cnt;
             if (part == 0) {
-              cand = first_standing<W>(sc.ent_key[i], sc.ent_len[i], eliminated);
-              cnt = sc.ent_cnt[i];
+              const Entry<W> en = sc.ent[i];
+              cand = first_standing<W>(en.key, en.len, eliminated);
+              cnt = en.cnt;
             } else {
               // an observed key stores at most nc-1 preferences; its length is implied by repetition
               cand = first_standing<W>(obs_key[i], nc - 1, eliminated);
