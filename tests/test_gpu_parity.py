@@ -593,6 +593,14 @@ def test_full_size_configs_conserve_ballots_and_agree_across_kernels(pkg, L, nam
         assert splits[2] < 50, splits
     for mode in (1, 2):
         assert res[0][0].tolist() == res[mode][0].tolist() and np.array_equal(res[0][1], res[mode][1]), mode
+    # the materialising path as one persistent kernel and as three launches per wave (whichever `auto` did not pick)
+    for phased in (0, 1):
+        t.tune(mode=0, sim_phased=phased)
+        w, o = t.sample_posterior_counts(n_el, cfg["n_ballots"], seed="FULL", return_orders=True)
+        launches = t.last_stats()["launches"]
+        assert (launches >= 3 and launches % 3 == 0) if phased else launches == 1, launches
+        assert w.tolist() == res[0][0].tolist() and np.array_equal(o, res[0][1]), phased
+    t.tune(sim_phased=-1)
     # the order reported for election 5 is one the reference rule allows on election 5's ballots
     ok, _ = oracle.load("port").irv_check_order((p, off), cnt, nc, res[1][1][5].astype(np.uint32))
     assert ok
