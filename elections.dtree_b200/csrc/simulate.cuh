@@ -1,23 +1,23 @@
-// simulate.cuh — the posterior-simulation kernel. One thread block simulates one election at a
-// time (persistent blocks pull election ids from a counter):
+// simulate.cuh — the materialising path: every sampled ballot of an election is created, then IRV runs over them.
+// Per election, three stages; simulate_kernel runs them in one persistent block per election, sim_big_kernel /
+// sim_walk_kernel / sim_irv_kernel run the same stages as three launches over a wave of elections (each at its own
+// register budget and occupancy), handing the counts over through a header in the election's scratch:
 //
-//   (a)+(b) level-synchronous expansion of the Dirichlet-tree (IRVNode::sample, irv_node.cpp:107-174,
-//           and lazyIRVBallots, :27-84). The frontier of one depth lives in a two-ended queue in
-//           global memory: items whose count is small enough for the Polya-urn shortcut grow from
-//           the front, the others from the back. Each WARP repeatedly claims a chunk of items and
-//           processes it on its own (no block barrier inside a level):
-//             - Gamma variates, one lane per (item, outcome), into a per-warp shared-memory tile;
-//             - a binary tree of partial sums over each item's outcomes (bottom-up), then the
-//               item's count is pushed down that tree with one binomial per internal node
-//               (top-down), again one lane per (item, tree node). This is rMultinomial
-//               (distributions.cpp:21-53) with the conditional binomials arranged as a balanced
-//               tree instead of a chain: the same multinomial law, log2(d) dependent steps instead
-//               of d-1, and no 1-x cancellation because both child sums are at hand;
-//             - children / finished ballots are compacted with warp ballots and appended to the
-//               next frontier / the entry list with one shared-memory atomic per warp and queue;
-//   (c)     IRV elimination over the election's (ballot, count) entries plus the shared observed
-//           entries (socialChoiceIRV, irv_ballot.cpp:42-138);
-//   (d)     win counts accumulated per block and flushed with one atomic per candidate.
+//   (a) level loop (IRVNode::sample, irv_node.cpp:107-174): items with more than urn_max ballots, level by level.
+//       Each WARP repeatedly claims a chunk of items and processes it on its own (no block barrier inside a level):
+//         - Gamma variates, one lane per (item, outcome), into a per-warp shared-memory tile;
+//         - a binary tree of partial sums over each item's outcomes (bottom-up), then the item's count is pushed down
+//           that tree with one binomial per internal node (top-down), again one lane per (item, tree node). This is
+//           rMultinomial (distributions.cpp:21-53) with the conditional binomials arranged as a balanced tree instead
+//           of a chain: the same multinomial law, log2(d) dependent steps instead of d-1, and no 1-x cancellation
+//           because both child sums are at hand;
+//         - children are compacted with warp ballots into the next frontier, finished ballots into the entry list,
+//           children with <= urn_max ballots into the election's small queue;
+//   (b) walkers (and lazyIRVBallots, :27-84): the small queue, every item an independent subtree of <= 8 ballots
+//       walked to completion with the Polya urn, from per-warp stacks in shared memory (walk_small_items);
+//   (c) IRV elimination over the election's (ballot, count) entries plus the shared observed entries
+//       (socialChoiceIRV, irv_ballot.cpp:42-138);
+//   (d) win counts accumulated per block and flushed with one atomic per candidate.
 #pragma once
 #include <cstdint>
 
@@ -38,7 +38,6 @@ constexpr int kClkSlots = 8;
 constexpr int kClkSlots = 0;
 #endif
 
-// Where the pieces of one block's scratch live.
 // One sampled (ballot, count) entry: a single 16-byte record for keys of one word (24 / 32 bytes for two / three), so that
 // writing an entry is one store and re-examining it in the IRV stage touches one 32-byte sector instead of three.
 template <int W>
@@ -50,6 +49,7 @@ struct alignas(W == 2 ? 8 : 16) Entry {
 
 static_assert(sizeof(Entry<1>) == 16 && sizeof(Entry<2>) == 24 && sizeof(Entry<3>) == 32, "capi.cu packs these records");
 
+// Where the pieces of one election's scratch live.
 template <int W>
 struct Scratch {
   uint32_t *hdr;       // kHdr* words: what one phase kernel hands to the next (phased launches)
