@@ -195,6 +195,7 @@ struct dtree {
   uint32_t last_lane_retries = 0;  // elections lane_kernel handed to its replay in the last call read back
   uint64_t mem_avail = 0;        // device bytes the plans may use (free + held by this handle), as last queried
   uint32_t lane_width = 0;  // lane_kernel: elections per warp (0: chosen per job)
+  uint32_t lane_block_warps = 0;  // lane_kernel: warps per block (0: chosen per job)
   int sim_phased = -1;  // materialising path as three launches per wave: -1 when it pays off, 0 never, 1 always
   int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
   // replicas on other devices for dtree_sample_posterior_multi (owned; same parameters, tree copied when stale)
@@ -617,7 +618,7 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
     pl.W = 1;
     pl.log_gamma = device_params(P).small_alpha != 0;
     pl.deferred = pl.lane = true;
-    pl.block = 128;
+    pl.block = kLaneBlock;
     pl.cap_items = 64;
     pl.cap_queue = 8;
     pl.cap_big = 16;
@@ -759,7 +760,7 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
     if (!hit || 4ull * z.lbig > 3ull * z.lane_big) z.lane_big = (uint32_t)std::min<uint64_t>(pl.arena_items, 2ull * z.lbig + 24);
     Plan lp = pl;
     lp.lane = true;
-    lp.block = 128;
+    lp.block = kLaneBlock;
     lp.cap_items = std::min(z.lane_pool, pl.arena_items);
     lp.cap_queue = std::min(z.lane_queue, pl.arena_queue);
     lp.cap_big = std::min(z.lane_big, pl.arena_items);
@@ -772,21 +773,28 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
       lp.cap_big = std::min(lp.cap_big, t->arena_cap);
     }
     lp.stride = (lane_scratch_bytes(lp.cap_items, lp.cap_queue, lp.cap_big) + 255) & ~255ull;  // per election
-    lp.stride_block = lp.stride * lp.block;
     {
-      int occ = lane_blocks_per_sm(device_params(P), pl.log_gamma);
-      if (occ <= 0) return fail(DTREE_ERR_CUDA, "lane kernel cannot be resident");
-      if (t->blocks_per_sm > 0) occ = std::min(occ, t->blocks_per_sm);
-      const uint64_t resident = (uint64_t)occ * t->sm_count;
-      const uint64_t fit = std::max<uint64_t>(1, pl.mem_budget / lp.stride_block);
+      int wps = lane_warps_per_sm(device_params(P), pl.log_gamma);  // resident warps per SM
+      if (wps <= 0) return fail(DTREE_ERR_CUDA, "lane kernel cannot be resident");
+      if (t->blocks_per_sm > 0) wps = std::min(wps, t->blocks_per_sm * (kLaneBlock / 32));
       // Elections per warp: 32 unless the tuning key lane_width says otherwise. Measured (tools/width_probe.py, C3): a
       // warp's batch takes ~0.4 ms however few of its lanes work (one election alone is a 0.25 ms chain of dependent
       // variates), so spreading a small job over more, narrower warps buys at most 5 % (12 500 elections: 0.436 ms at
       // 32 per warp, 0.412 at 8, 0.53 at 4) and costs a lot once the warps outnumber the schedulers' appetite.
       const uint64_t todo = (uint64_t)(n_elections - pilot_done);
       lp.lane_width = t->lane_width ? t->lane_width : 32u;
-      const uint64_t per_block = (uint64_t)lp.lane_width * (lp.block / 32);
-      const uint64_t need = (todo + per_block - 1) / per_block;
+      const uint64_t batches = (todo + lp.lane_width - 1) / lp.lane_width;  // one per warp and claim
+      // Blocks: ONE per SM, of as many warps as the job needs to run in a single pass (at most `wps`, and what the
+      // memory budget allows); a job larger than that runs on full blocks whose warps claim batch after batch.
+      const uint64_t fit_warps = std::max<uint64_t>(1, pl.mem_budget / (lp.stride * 32));
+      const uint64_t sms = (uint64_t)t->sm_count;
+      uint64_t wpb = std::min<uint64_t>((uint64_t)wps, std::max<uint64_t>(1, (batches + sms - 1) / sms));
+      if (t->lane_block_warps) wpb = std::min<uint64_t>((uint64_t)wps, t->lane_block_warps);
+      wpb = std::max<uint64_t>(1, std::min(wpb, fit_warps));
+      const uint64_t fit = std::max<uint64_t>(1, fit_warps / wpb), resident = sms * ((uint64_t)wps / wpb);
+      const uint64_t need = (batches + wpb - 1) / wpb;
+      lp.block = (int)(wpb * 32);
+      lp.stride_block = lp.stride * lp.block;
       lp.grid = (int)std::max<uint64_t>(1, std::min(std::min(resident, fit), need));
       if (t->mode < 0) {
         // Automatic choice: a thread per election pays off when there are enough elections to fill the machine
@@ -1334,6 +1342,7 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
     r->build_mode = t->build_mode;
     r->sim_phased = t->sim_phased;
     r->lane_width = t->lane_width;
+    r->lane_block_warps = t->lane_block_warps;
     r->mode = t->mode;
     r->urn_max = t->urn_max;
     r->block_threads = t->block_threads;
@@ -1605,6 +1614,9 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   } else if (!strcmp(key, "lane_max_splits")) {
     if (value < -1) return fail(DTREE_ERR_ARG, "lane_max_splits must be -1 (auto), 0 (no limit) or a positive count");
     t->lane_max_splits = value;
+  } else if (!strcmp(key, "lane_block_warps")) {
+    if (value < 0 || value > kLaneMaxBlock / 32) return fail(DTREE_ERR_ARG, "lane_block_warps must be 0 (auto) or 1..24");
+    t->lane_block_warps = (uint32_t)value;
   } else if (!strcmp(key, "lane_width")) {
     if (value < 0 || value > 32) return fail(DTREE_ERR_ARG, "lane_width must be 0 (auto) or 1..32");
     t->lane_width = (uint32_t)value;

@@ -11,7 +11,7 @@ static uint32_t lane_tile_leaves(const DeviceParams &P) {
   return dp;
 }
 
-size_t lane_smem_bytes(const DeviceParams &P) { return (size_t)(128 / 32) * LaneShared::bytes(P.nc, lane_tile_leaves(P)); }
+static size_t lane_smem_bytes_per_warp(const DeviceParams &P) { return LaneShared::bytes(P.nc, lane_tile_leaves(P)); }
 
 uint64_t lane_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t cap_big) {
   return LaneScratch::bytes(cap_items, cap_queue, cap_big);
@@ -19,26 +19,30 @@ uint64_t lane_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t cap
 
 template <bool LOG>
 static cudaError_t prepare(size_t smem) {
-  return cudaFuncSetAttribute(lane_kernel<128, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaFuncSetAttribute(lane_kernel<kLaneMaxBlock, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 cudaError_t launch_lane(const SimArgs &a, const LaunchCfg &cfg) {
-  if (cfg.block != 128) return cudaErrorInvalidValue;
-  const size_t smem = lane_smem_bytes(a.P);
+  if (cfg.block < 32 || cfg.block > kLaneMaxBlock || cfg.block % 32) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(cfg.block / 32) * lane_smem_bytes_per_warp(a.P);
   cudaError_t e = cfg.log_gamma ? prepare<true>(smem) : prepare<false>(smem);
   if (e != cudaSuccess) return e;
-  if (cfg.log_gamma) lane_kernel<128, true><<<cfg.grid, 128, smem, cfg.stream>>>(a);
-  else lane_kernel<128, false><<<cfg.grid, 128, smem, cfg.stream>>>(a);
+  if (cfg.log_gamma) lane_kernel<kLaneMaxBlock, true><<<cfg.grid, cfg.block, smem, cfg.stream>>>(a);
+  else lane_kernel<kLaneMaxBlock, false><<<cfg.grid, cfg.block, smem, cfg.stream>>>(a);
   return cudaGetLastError();
 }
 
-int lane_blocks_per_sm(const DeviceParams &P, bool lg) {
-  const size_t smem = lane_smem_bytes(P);
+int lane_warps_per_sm(const DeviceParams &P, bool lg) {
+  // asked in blocks of one warp: the answer is then limited by registers and shared memory per warp alone
+  const size_t smem = lane_smem_bytes_per_warp(P);
   if ((lg ? prepare<true>(smem) : prepare<false>(smem)) != cudaSuccess) return 0;
   int n = 0;
-  cudaError_t e = lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lane_kernel<128, true>, 128, smem)
-                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lane_kernel<128, false>, 128, smem);
-  return e == cudaSuccess ? n : 0;
+  cudaError_t e = lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lane_kernel<kLaneMaxBlock, true>, 32, smem)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lane_kernel<kLaneMaxBlock, false>, 32, smem);
+  if (e != cudaSuccess) return 0;
+  return n < kLaneMaxBlock / 32 ? n : kLaneMaxBlock / 32;
 }
+
+int lane_blocks_per_sm(const DeviceParams &P, bool lg) { return lane_warps_per_sm(P, lg) / (kLaneBlock / 32); }
 
 }  // namespace dtb

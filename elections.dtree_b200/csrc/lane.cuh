@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(BLOCK, DTB_LANE_THREADS_PER_SM / BLOCK) lane_k
   sh.bind(lane_smem + (size_t)warp * LaneShared::bytes(nc, dp_max), nc);
   const DeferredCaps cp{a.cap_items, a.cap_queue, a.cap_big};
   LaneScratch sc;
-  sc.bind(a.scratch + ((uint64_t)blockIdx.x * (BLOCK / 32) + warp) * 32ull * a.scratch_stride, cp.pool, cp.queue, cp.big, lane);
+  sc.bind(a.scratch + ((uint64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32ull * a.scratch_stride, cp.pool, cp.queue, cp.big, lane);
   uint32_t stat[kStatCount], usage[3] = {0u, 0u, 0u};
 #pragma unroll
   for (int i = 0; i < kStatCount; ++i) stat[i] = 0;
