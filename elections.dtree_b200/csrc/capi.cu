@@ -196,6 +196,7 @@ struct dtree {
   uint64_t mem_avail = 0;        // device bytes the plans may use (free + held by this handle), as last queried
   uint32_t lane_width = 0;  // lane_kernel: elections per warp (0: chosen per job)
   uint32_t lane_block_warps = 0;  // lane_kernel: warps per block (0: chosen per job)
+  int lane_sync = -1;  // lane_kernel: block-wide meeting points (-1 chosen per job, 0 none, 1 claim + after the root split, 2 + every round, 3 + every split step)
   int sim_phased = -1;  // materialising path as three launches per wave: -1 when it pays off, 0 never, 1 always
   int mode = -1;  // 0: materialise every ballot (simulate_kernel); 1: deferred expansion (deferred_kernel); -1: choose
   // replicas on other devices for dtree_sample_posterior_multi (owned; same parameters, tree copied when stale)
@@ -469,6 +470,7 @@ void fill_args(dtree *t, const Plan &pl, SimArgs &a) {
   a.cap_items = pl.cap_items;
   a.cap_small = pl.cap_small;
   a.lane_width = pl.lane_width;
+  a.lane_sync = t->lane_sync >= 0 ? (uint32_t)t->lane_sync : (pl.lane && pl.block >= 512 ? 2u : 0u);
   a.cap_entries = pl.cap_entries;
   a.cap_queue = pl.cap_queue;
   a.cap_big = pl.cap_big;
@@ -1343,6 +1345,7 @@ int dtree_sample_posterior_multi(dtree_t *t, const int *devices, int n_devices, 
     r->sim_phased = t->sim_phased;
     r->lane_width = t->lane_width;
     r->lane_block_warps = t->lane_block_warps;
+    r->lane_sync = t->lane_sync;
     r->mode = t->mode;
     r->urn_max = t->urn_max;
     r->block_threads = t->block_threads;
@@ -1614,6 +1617,9 @@ int dtree_set_tuning(dtree_t *t, const char *key, int64_t value) {
   } else if (!strcmp(key, "lane_max_splits")) {
     if (value < -1) return fail(DTREE_ERR_ARG, "lane_max_splits must be -1 (auto), 0 (no limit) or a positive count");
     t->lane_max_splits = value;
+  } else if (!strcmp(key, "lane_sync")) {
+    if (value < -1 || value > 3) return fail(DTREE_ERR_ARG, "lane_sync must be -1 (auto) or 0..3");
+    t->lane_sync = (int)value;
   } else if (!strcmp(key, "lane_block_warps")) {
     if (value < 0 || value > kLaneMaxBlock / 32) return fail(DTREE_ERR_ARG, "lane_block_warps must be 0 (auto) or 1..24");
     t->lane_block_warps = (uint32_t)value;

@@ -341,9 +341,14 @@ __global__ void __launch_bounds__(BLOCK, DTB_LANE_THREADS_PER_SM / BLOCK) lane_k
     uint32_t base = 0;
     if (lane == 0u) base = atomicAdd(a.work_counter, a.lane_width);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= a.n_elections) break;
+    if (a.lane_sync) {
+      // the warps of the block go through their batches together (a warp without one idles through the barriers)
+      if (__syncthreads_and(base >= a.n_elections)) break;
+    } else if (base >= a.n_elections) {
+      break;
+    }
     const uint32_t e = base + lane;
-    const bool active = lane < a.lane_width && e < a.n_elections;
+    const bool active = lane < a.lane_width && e < a.n_elections && base < a.n_elections;
     const RngKey key = election_key(a.seed, a.first_election + e);
     LaneState st;
     st.n_pool = 0; st.n_free = 0; st.q_head = 0; st.q_tail = 0; st.n_big = 0; st.n_top = 0; st.eliminated = 0;
@@ -391,6 +396,7 @@ __global__ void __launch_bounds__(BLOCK, DTB_LANE_THREADS_PER_SM / BLOCK) lane_k
       root.pad_ = 0;
       split_node(active, root);  // the root holds every ballot: split at once
     }
+    if (a.lane_sync) __syncthreads();
     if (a.sc_function == 1) {
       // Plurality (R/social_choice.R:58-83): the candidates with the most first preferences, all of them when tied.
       // First preferences are the root's split plus the observed first preferences that rode along: nothing below
@@ -407,6 +413,7 @@ __global__ void __launch_bounds__(BLOCK, DTB_LANE_THREADS_PER_SM / BLOCK) lane_k
       continue;
     }
     for (uint32_t round = 0; round < n_rounds; ++round) {
+      if (a.lane_sync > 1u) __syncthreads();
       bool pending = !decided && !st.overflow;  // this lane still has to settle the round
       for (;;) {
         bool uncertain = false;
@@ -468,7 +475,7 @@ __global__ void __launch_bounds__(BLOCK, DTB_LANE_THREADS_PER_SM / BLOCK) lane_k
             }
           }
         }
-        if (!__any_sync(0xffffffffu, uncertain)) break;
+        if (a.lane_sync > 2u ? !__syncthreads_or(uncertain) : !__any_sync(0xffffffffu, uncertain)) break;
         if (uncertain && !st.overflow && a.lane_max_splits != 0u && ++st.n_splits > a.lane_max_splits)
           st.overflow = true;  // a heavy election: a whole warp finishes it faster (replayed by deferred_kernel)
         const bool want = uncertain && !st.overflow;

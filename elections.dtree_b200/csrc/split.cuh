@@ -69,6 +69,7 @@ struct SimArgs {
   unsigned int *retry_count;
   uint32_t retry_cap;
   uint32_t tau_quarters;           // deferred_kernel: share (in quarters) of the missing margin that may keep waiting (1..3)
+  uint32_t lane_sync;              // lane_kernel: 0 warps run free; 1 the block claims together and meets after the root split; 2 and at every round; 3 and at every split step
   uint32_t lane_width;             // lane_kernel: elections a warp claims at a time (1..32 lanes of it work)
   uint32_t lane_max_splits;        // lane_kernel: an election that needs more node splits goes to the retry list (0: no limit)
   // outputs

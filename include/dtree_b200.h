@@ -217,7 +217,10 @@ int dtree_set_abort_callback(dtree_t *t, int (*should_abort)(void *), void *user
  *      "lane_width" (0 default = 32; 1..32 = elections a warp of mode 2 claims at a time, the other lanes idle: a
  *        measurement hook for small jobs; results do not change);
  *      "lane_block_warps" (0 default = as many warps per block as make the job one block per SM, at most 24; 1..24 =
- *        warps per block of mode 2; results do not change).
+ *        warps per block of mode 2; results do not change);
+ *      "lane_sync" (-1 default: 2 for blocks of 16 warps and more, else 0; 0..3 = how often the warps of a mode-2 block
+ *        wait for each other: never / when they claim elections and after the root split / also at every IRV round /
+ *        also at every node split. Warps that stay together share the instruction cache; results do not change).
  * Returns DTREE_ERR_ARG for an unknown key. */
 int dtree_set_tuning(dtree_t *t, const char *key, int64_t value);
 /* Statistics of the last sampling call on this handle (counters restart at every call; [7] and [14] describe the
