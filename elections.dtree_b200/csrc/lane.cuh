@@ -314,7 +314,7 @@ __device__ void lane_split_big(const SimArgs &a, const LaneShared &sh, uint32_t 
 #define DTB_LANE_THREADS_PER_SM 768
 #endif
 template <int BLOCK, bool LOG>
-__global__ void __launch_bounds__(BLOCK, DTB_LANE_THREADS_PER_SM / BLOCK) lane_kernel(const __grid_constant__ SimArgs a) {
+__global__ void __launch_bounds__(BLOCK, DTB_LANE_THREADS_PER_SM / BLOCK > 0 ? DTB_LANE_THREADS_PER_SM / BLOCK : 1) lane_kernel(const __grid_constant__ SimArgs a) {
   extern __shared__ __align__(16) uint8_t lane_smem[];
   __shared__ uint32_t s_wins[kMaxCandidates];
   const int tid = threadIdx.x;

@@ -36,7 +36,10 @@ uint64_t deferred_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t
 // threads (one block fills an SM's register file at 80 registers per thread); launched with any multiple of 32 up to that.
 // A job that fits the machine in one pass runs as ONE block per SM of as many warps as it takes (warps of a block start
 // together and stay close in the instruction stream: measured 6 % faster than six 128-thread blocks per SM).
-constexpr int kLaneMaxBlock = 768;
+#ifndef DTB_LANE_MAX_BLOCK
+#define DTB_LANE_MAX_BLOCK 768
+#endif
+constexpr int kLaneMaxBlock = DTB_LANE_MAX_BLOCK;
 constexpr int kLaneBlock = 128;  // block size of the plurality launches (root split only)
 cudaError_t launch_lane(const SimArgs &a, const LaunchCfg &cfg);
 int lane_warps_per_sm(const DeviceParams &P, bool log_gamma);  // resident warps per SM (registers, shared memory)
