@@ -142,11 +142,14 @@ struct dtree_ballots {
   std::vector<uint32_t> counts;
 };
 
+constexpr uint32_t kLenNone = 0xFFFFFFFFu, kLenMixed = 0xFFFFFFFEu;
+
 struct dtree {
   // Observed ballots as given to dtree_update (validated): the device builds the tree from this log
   // (tree_build.cu); the host trie below is brought up to date only for the host-side exports.
   std::vector<uint8_t> log_prefs;
   std::vector<uint64_t> log_offsets{0};
+  uint32_t log_len = kLenNone;  // common number of preferences of the ballots in the log (kLenNone: empty, kLenMixed)
   PinnedRange pin_prefs, pin_offsets;  // the two vectors' buffers while page-locked (dropped before they can move)
   uint64_t n_observed = 0, depth_mask = 0, version = 0;  // version: bumped by update/reset
   HostTree tree;              // parameters (tree.P) + lazily synchronised trie
@@ -280,7 +283,7 @@ int ensure_mirror(dtree *t, cudaStream_t s) {
     bool too_big = false;
     CUDA_TRY(build_tree_on_device(t->dev, t->tree.P.nc, t->log_prefs.data(), t->log_offsets.data(),
                                   t->log_offsets.size() - 1, s, &bs, &too_big, t->build_mode == 2 ? 0ull : 1ull << 30,
-                                  t->build_mode == 0));
+                                  t->build_mode == 0, t->log_len < kLenMixed ? t->log_len : 0xFFFFFFFFu));
     if (too_big) return fail(DTREE_ERR_STATE, "tree has too many outcome slots for 32-bit indices");
     t->stats[kOutH2D] += bs.h2d_bytes;
     t->stats[kOutBuildLaunches] = bs.launches;
@@ -1135,7 +1138,12 @@ int dtree_update(dtree_t *t, const uint8_t *prefs, const uint64_t *offsets, uint
   const uint64_t at = t->log_prefs.size(), first = offsets[0];
   if (at + (offsets[n] - first) > t->log_prefs.capacity() || t->log_offsets.size() + n > t->log_offsets.capacity()) unpin_log(t);
   t->log_prefs.insert(t->log_prefs.end(), prefs + first, prefs + offsets[n]);
-  for (uint64_t i = 1; i <= n; ++i) t->log_offsets.push_back(at + (offsets[i] - first));
+  for (uint64_t i = 1; i <= n; ++i) {
+    t->log_offsets.push_back(at + (offsets[i] - first));
+    const uint64_t len = offsets[i] - offsets[i - 1];
+    if (t->log_len == kLenNone) t->log_len = (uint32_t)len;
+    else if (t->log_len != (uint32_t)len) t->log_len = kLenMixed;
+  }
   t->n_observed += n;  // R_tree.cpp:149
   t->depth_mask |= mask;
   ++t->version;
@@ -1146,6 +1154,7 @@ int dtree_reset(dtree_t *t) {
   if (!t) return fail(DTREE_ERR_ARG, "null handle");
   t->log_prefs.clear();
   t->log_offsets.assign(1, 0);
+  t->log_len = kLenNone;
   t->n_observed = t->depth_mask = 0;
   t->tree.reset();
   t->trie_ballots = 0;

@@ -654,9 +654,15 @@ cudaError_t grow_slots(DeviceTreeStore &S, size_t slots, size_t keep, cudaStream
 
 }  // namespace
 
+// off[i] = i * len for i in [first, last]: the offsets of a log whose ballots all have `len` preferences.
+__global__ void uniform_offsets_kernel(uint64_t *off, uint64_t first, uint64_t last, uint32_t len) {
+  const uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= last) off[i] = i * len;
+}
+
 cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t *h_prefs, const uint64_t *h_offsets,
                                  uint64_t n_ballots, cudaStream_t stream, BuildStats *stats, bool *too_big,
-                                 uint64_t bound_budget_bytes, bool allow_cooperative) {
+                                 uint64_t bound_budget_bytes, bool allow_cooperative, uint32_t uniform_len) {
   const int W = key_words_for(nc);
   BuildStats st;
   if (too_big) *too_big = false;
@@ -680,9 +686,16 @@ cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t 
     BUILD_TRY(S.log_off.grow(n_ballots + 1, old_b + 1, stream));
     if (bytes > old_bytes)
       BUILD_TRY(cudaMemcpyAsync(S.log_prefs.p + old_bytes, h_prefs + old_bytes, bytes - old_bytes, cudaMemcpyHostToDevice, stream));
-    BUILD_TRY(cudaMemcpyAsync(S.log_off.p + old_b, h_offsets + old_b, (n_ballots - old_b + 1) * sizeof(uint64_t),
-                              cudaMemcpyHostToDevice, stream));
-    st.h2d_bytes += (bytes - old_bytes) + (n_ballots - old_b + 1) * sizeof(uint64_t);
+    if (uniform_len != 0xFFFFFFFFu) {
+      const uint64_t cnt = n_ballots - old_b + 1;
+      uniform_offsets_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(S.log_off.p, old_b, n_ballots, uniform_len);
+      ++st.launches;
+      st.h2d_bytes += bytes - old_bytes;
+    } else {
+      BUILD_TRY(cudaMemcpyAsync(S.log_off.p + old_b, h_offsets + old_b, (n_ballots - old_b + 1) * sizeof(uint64_t),
+                                cudaMemcpyHostToDevice, stream));
+      st.h2d_bytes += (bytes - old_bytes) + (n_ballots - old_b + 1) * sizeof(uint64_t);
+    }
     first_new = old_b;
     slots_pending = true;
     S.log_ballots = n_ballots;

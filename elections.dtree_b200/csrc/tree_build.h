@@ -44,9 +44,11 @@ struct BuildStats {
 // min(#ballots, parents x children) nodes) fit `bound_budget_bytes`, the whole build is ONE cooperative kernel
 // (grid-wide barriers between the phases of every level) or, with allow_cooperative = false, the same phases as ~4
 // launches per level enqueued without a host round trip; otherwise the host reads every level's size to allocate
-// exactly.
+// exactly. uniform_len: every ballot of the log has that many preferences (UINT32_MAX: lengths differ): the offsets are
+// then written by a kernel instead of being uploaded (8 bytes per ballot of host-to-device traffic saved).
 cudaError_t build_tree_on_device(DeviceTreeStore &S, uint32_t nc, const uint8_t *h_prefs, const uint64_t *h_offsets,
                                  uint64_t n_ballots, cudaStream_t stream, BuildStats *stats, bool *too_big,
-                                 uint64_t bound_budget_bytes = 1ull << 30, bool allow_cooperative = true);
+                                 uint64_t bound_budget_bytes = 1ull << 30, bool allow_cooperative = true,
+                                 uint32_t uniform_len = 0xFFFFFFFFu);
 
 }  // namespace dtb

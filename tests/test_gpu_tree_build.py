@@ -137,6 +137,39 @@ def test_incremental_updates_reset_and_empty_tree(pkg, L, port):
     o.close()
 
 
+def test_log_of_equal_length_ballots_needs_no_offsets_upload(pkg, L, port):
+    """While every ballot of the log has the same number of preferences the device writes the offsets itself
+    (8 bytes per ballot less to upload); the first ballot of another length switches back to uploading them. Same tree
+    either way, also after dtree_invalidate_device (the whole log from host memory again) and after a reset."""
+    from elections_dtree_b200 import _native as N
+    nc = 7
+    rng = np.random.default_rng(23)
+    dev, host = build_both(pkg, nc, [])
+    o = port.tree(nc, 0, nc, 1.0, False)
+
+    def full(n):
+        w = np.exp(-0.5 * np.arange(nc))
+        return [tuple(int(c) for c in np.argsort(-(rng.gumbel(size=nc) + np.log(w)))) for _ in range(n)]
+
+    for step, ballots in enumerate([full(500), full(300), ragged_ballots(rng, nc, 200), full(100)]):
+        prefs, offsets = oracle.ballots_to_csr(ballots)
+        dev.update_indices(prefs, offsets)
+        host.update_indices(prefs, offsets)
+        o.update((prefs, offsets))
+        img = dev.device_image()
+        assert oracle.parse_node_dump(image_to_node_dump(img, nc)) == oracle.parse_node_dump(o.dump_nodes()), step
+        assert_same_image(img, host.device_image())
+        N.check(L.dtree_invalidate_device(dev._h))
+        assert_same_image(dev.device_image(), img)
+    dev.reset()
+    host.reset()
+    prefs, offsets = oracle.ballots_to_csr(full(64))
+    dev.update_indices(prefs, offsets)
+    host.update_indices(prefs, offsets)
+    assert_same_image(dev.device_image(), host.device_image())
+    o.close()
+
+
 @pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5"])
 def test_benchmark_trees_match_the_host_trie_and_sample_identically(pkg, L, name):
     W = pkg.workloads
