@@ -623,16 +623,19 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
     pl.W = 1;
     pl.log_gamma = device_params(P).small_alpha != 0;
     pl.deferred = pl.lane = true;
-    pl.block = kLaneBlock;
     pl.cap_items = 64;
     pl.cap_queue = 8;
     pl.cap_big = 16;
     pl.stride = (lane_scratch_bytes(pl.cap_items, pl.cap_queue, pl.cap_big) + 255) & ~255ull;
-    pl.stride_block = pl.stride * pl.block;
-    int occ = lane_blocks_per_sm(device_params(P), pl.log_gamma);
-    if (occ <= 0) return fail(DTREE_ERR_CUDA, "lane kernel cannot be resident");
-    const uint64_t need = ((uint64_t)n_elections + pl.block - 1) / pl.block;
-    pl.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)occ * t->sm_count, need));
+    const int wps = lane_warps_per_sm(device_params(P), pl.log_gamma);
+    if (wps <= 0) return fail(DTREE_ERR_CUDA, "lane kernel cannot be resident");
+    {  // one block per SM of as many warps as the job needs, as for IRV (below)
+      const uint64_t batches = ((uint64_t)n_elections + 31) / 32, sms = (uint64_t)t->sm_count;
+      const uint64_t wpb = std::min<uint64_t>((uint64_t)wps, std::max<uint64_t>(1, (batches + sms - 1) / sms));
+      pl.block = (int)(wpb * 32);
+      pl.stride_block = pl.stride * pl.block;
+      pl.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(sms * ((uint64_t)wps / wpb), (batches + wpb - 1) / wpb));
+    }
     CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));
     CUDA_TRY(t->d_retry.reserve(8));
     SimArgs &a = j.a;

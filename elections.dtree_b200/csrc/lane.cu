@@ -43,6 +43,4 @@ int lane_warps_per_sm(const DeviceParams &P, bool lg) {
   return n < kLaneMaxBlock / 32 ? n : kLaneMaxBlock / 32;
 }
 
-int lane_blocks_per_sm(const DeviceParams &P, bool lg) { return lane_warps_per_sm(P, lg) / (kLaneBlock / 32); }
-
 }  // namespace dtb

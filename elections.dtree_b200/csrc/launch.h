@@ -40,10 +40,9 @@ uint64_t deferred_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t
 #define DTB_LANE_MAX_BLOCK 768
 #endif
 constexpr int kLaneMaxBlock = DTB_LANE_MAX_BLOCK;
-constexpr int kLaneBlock = 128;  // block size of the plurality launches (root split only)
+constexpr int kLaneBlock = 128;  // the unit the tuning key blocks_per_sm counts in (round-1 block size)
 cudaError_t launch_lane(const SimArgs &a, const LaunchCfg &cfg);
 int lane_warps_per_sm(const DeviceParams &P, bool log_gamma);  // resident warps per SM (registers, shared memory)
-int lane_blocks_per_sm(const DeviceParams &P, bool log_gamma);  // ... in blocks of kLaneBlock threads
 uint64_t lane_scratch_bytes(uint32_t cap_items, uint32_t cap_queue, uint32_t cap_big);  // per election
 
 // Stand-alone IRV over entries already placed in block 0's scratch (dtree_irv).
