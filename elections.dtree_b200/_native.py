@@ -75,6 +75,7 @@ _SIGS = {
     "dtree_debug_binomial_ex": (C.c_int, [C.c_uint32, C.c_double, C.c_uint64, C.c_uint32, u32p, C.c_int, C.c_int]),
     "dtree_debug_binv_law": (C.c_int, [C.c_uint32, C.c_double, u32p, C.c_int]),
     "dtree_debug_device_image": (C.c_int, [vp, C.c_int, vp, C.c_uint64, u64p]),
+    "dtree_debug_lane_shape": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, u32p, u32p]),
 }
 
 _lib = None

@@ -18,6 +18,7 @@
 #include "dtree_b200_debug.h"
 #include "host_tree.h"
 #include "launch.h"
+#include "launch_shape.h"
 #include "tree_build.h"
 
 using namespace dtb;
@@ -629,12 +630,11 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
     pl.stride = (lane_scratch_bytes(pl.cap_items, pl.cap_queue, pl.cap_big) + 255) & ~255ull;
     const int wps = lane_warps_per_sm(device_params(P), pl.log_gamma);
     if (wps <= 0) return fail(DTREE_ERR_CUDA, "lane kernel cannot be resident");
-    {  // one block per SM of as many warps as the job needs, as for IRV (below)
-      const uint64_t batches = ((uint64_t)n_elections + 31) / 32, sms = (uint64_t)t->sm_count;
-      const uint64_t wpb = std::min<uint64_t>((uint64_t)wps, std::max<uint64_t>(1, (batches + sms - 1) / sms));
-      pl.block = (int)(wpb * 32);
+    {  // one block per SM of as many warps as the job needs, as for IRV (below); the token arenas always fit
+      const LaneShape shape = lane_shape(((uint64_t)n_elections + 31) / 32, (uint32_t)t->sm_count, (uint32_t)wps, ~0ull, 0);
+      pl.block = (int)(shape.warps_per_block * 32);
       pl.stride_block = pl.stride * pl.block;
-      pl.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(sms * ((uint64_t)wps / wpb), (batches + wpb - 1) / wpb));
+      pl.grid = (int)shape.grid;
     }
     CUDA_TRY(t->d_scratch.reserve(pl.stride_block * pl.grid));
     CUDA_TRY(t->d_retry.reserve(8));
@@ -795,15 +795,12 @@ int job_prepare(Job &j, dtree *t, uint64_t first_election, uint32_t n_elections,
       // Blocks: ONE per SM, of as many warps as the job needs to run in a single pass (at most `wps`, and what the
       // memory budget allows); a job larger than that runs on full blocks whose warps claim batch after batch.
       const uint64_t fit_warps = std::max<uint64_t>(1, pl.mem_budget / (lp.stride * 32));
-      const uint64_t sms = (uint64_t)t->sm_count;
-      uint64_t wpb = std::min<uint64_t>((uint64_t)wps, std::max<uint64_t>(1, (batches + sms - 1) / sms));
-      if (t->lane_block_warps) wpb = std::min<uint64_t>((uint64_t)wps, t->lane_block_warps);
-      wpb = std::max<uint64_t>(1, std::min(wpb, fit_warps));
-      const uint64_t fit = std::max<uint64_t>(1, fit_warps / wpb), resident = sms * ((uint64_t)wps / wpb);
-      const uint64_t need = (batches + wpb - 1) / wpb;
+      const LaneShape shape = lane_shape(batches, (uint32_t)t->sm_count, (uint32_t)wps, fit_warps, t->lane_block_warps);
+      const uint64_t wpb = shape.warps_per_block;
+      const uint64_t fit = std::max<uint64_t>(1, fit_warps / wpb), resident = (uint64_t)t->sm_count * ((uint64_t)wps / wpb);
       lp.block = (int)(wpb * 32);
       lp.stride_block = lp.stride * lp.block;
-      lp.grid = (int)std::max<uint64_t>(1, std::min(std::min(resident, fit), need));
+      lp.grid = (int)shape.grid;
       if (t->mode < 0) {
         // Automatic choice: a thread per election pays off when there are enough elections to fill the machine
         // (a thread runs its election alone, start to finish) and memory lets most of the threads be resident.

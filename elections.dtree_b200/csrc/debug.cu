@@ -4,6 +4,7 @@
 #include "dtree_b200.h"
 #include "dtree_b200_debug.h"
 #include "host_tree.h"
+#include "launch_shape.h"
 #include "variates.cuh"
 
 using namespace dtb;
@@ -61,6 +62,15 @@ int cuda_fail(const char *what, cudaError_t e) {
 }  // namespace
 
 extern "C" {
+
+int dtree_debug_lane_shape(uint64_t batches, uint32_t sms, uint32_t warps_per_sm, uint64_t fit_warps, uint32_t forced_wpb,
+                           uint32_t *warps_per_block, uint32_t *grid) {
+  if (!warps_per_block || !grid) return DTREE_ERR_ARG;
+  const LaneShape s = lane_shape(batches, sms, warps_per_sm, fit_warps, forced_wpb);
+  *warps_per_block = s.warps_per_block;
+  *grid = s.grid;
+  return DTREE_OK;
+}
 
 int dtree_debug_philox(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4], int on_device) {
   U4 c{counter[0], counter[1], counter[2], counter[3]};

@@ -32,6 +32,12 @@ int dtree_debug_binomial_ex(uint32_t n_trials, double p, uint64_t seed, uint32_t
  * give k (k <= 192). Divided by 2^23 this is the sampler's exact output law, to compare with the binomial pmf. */
 int dtree_debug_binv_law(uint32_t n_trials, double p, uint32_t counts[256], int device);
 
+/* Launch shape of a thread-per-election job (csrc/launch_shape.h; host arithmetic, no device needed): `batches` units of
+ * 32 elections on `sms` multiprocessors that hold `warps_per_sm` warps of the kernel each, scratch for `fit_warps`
+ * warps, tuning key lane_block_warps = forced_wpb (0: automatic). */
+int dtree_debug_lane_shape(uint64_t batches, uint32_t sms, uint32_t warps_per_sm, uint64_t fit_warps, uint32_t forced_wpb,
+                           uint32_t *warps_per_block, uint32_t *grid);
+
 /* Copies one array of the handle's device mirror back to the host (building the mirror first if it is
  * stale). which: 0 node_base u32[n_nodes+1], 1 node_total u32[n_nodes], 2 slot_count u32[n_slots],
  * 3 slot_child i32[n_slots], 4 slot_cand u8[n_slots], 5 obs_key u64[n_obs*W], 6 obs_cnt u32[n_obs],

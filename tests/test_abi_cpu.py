@@ -305,3 +305,40 @@ def test_update_property_random_ballot_streams(pkg, port):
         o.close()
 
     check()
+
+
+def test_lane_kernel_launch_shape(pkg):
+    """csrc/launch_shape.h: a thread-per-election job is launched as ONE block per SM of as many warps as it needs to run
+    in a single pass, never more warps than an SM holds or than have scratch, and the grid always covers the job or
+    fills the machine (the warps then claim batch after batch)."""
+    import ctypes as C
+    L = pkg._native.lib()
+
+    def shape(batches, sms=148, wps=24, fit=10**9, forced=0):
+        w, g = C.c_uint32(0), C.c_uint32(0)
+        assert L.dtree_debug_lane_shape(batches, sms, wps, fit, forced, C.byref(w), C.byref(g)) == 0
+        return w.value, g.value
+
+    # the benchmark job: 100 000 elections = 3 125 batches -> 22 warps per block, 143 blocks (one per SM, one pass)
+    assert shape(3125) == (22, 143)
+    # 12 500 elections: 3 warps per block on 131 SMs; a tiny job: single-warp blocks
+    assert shape(391) == (3, 131)
+    assert shape(5) == (1, 5)
+    # larger than one pass: full blocks on every SM
+    assert shape(31250) == (24, 148)
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        batches = int(rng.integers(1, 200000))
+        sms = int(rng.integers(1, 200))
+        wps = int(rng.integers(1, 25))
+        fit = int(rng.integers(1, 6000))
+        forced = int(rng.choice([0, 0, 0, int(rng.integers(1, 25))]))
+        w, g = shape(batches, sms, wps, fit, forced)
+        assert 1 <= w <= wps and w <= fit and g >= 1
+        assert w * g <= max(fit, w)                      # never more warps than have scratch
+        assert g <= sms * (wps // w)                     # never more blocks than are resident
+        covers = w * g >= batches
+        full = g == min(sms * (wps // w), max(1, fit // w))
+        assert covers or full                            # one pass, or the machine (or the memory budget) is full
+        if forced == 0 and covers and fit >= sms * wps:
+            assert g <= sms                              # one block per SM when the job fits one pass
